@@ -1,0 +1,117 @@
+#!/usr/bin/env python3
+"""Copy the reference's HOST decoder sources into a scratch directory and cut the B200 seams.
+
+The product keeps the reference's bitstream parser (north star: "bitstream parsing stays in
+C on the host").  Nothing from the reference is committed to this repository: this script
+copies the needed files from <reference_root> into <out_dir> at build time and applies
+anchor-based edits (each anchor must match exactly once, otherwise the build fails loudly,
+so a drifted reference cannot be patched silently).  The edits are the reference-side
+binding INTEGRATION.md documents; every inserted line calls into hostdec/vp8b200_seam.c.
+
+usage: apply_seams.py <reference_root> <out_dir>
+"""
+import os
+import shutil
+import sys
+
+# directories / files of the reference the host decoder build needs
+COPY = ["vp8/common", "vp8/decoder", "vp8/vp8_dx_iface.c", "vpx", "vpx_mem", "vpx_ports",
+        "vpx_scale", "vpxdec.c", "md5_utils.c", "md5_utils.h", "args.c", "args.h",
+        "tools_common.c", "tools_common.h", "nestegg"]
+
+INC = '#include "vp8b200_seam.h"\n'
+
+
+def find_one(lines, needle, start=0):
+    hits = [i for i in range(start, len(lines)) if needle in lines[i]]
+    if len(hits) != 1:
+        raise SystemExit("apply_seams: anchor %r matched %d times" % (needle, len(hits)))
+    return hits[0]
+
+
+def patch(path, fn):
+    with open(path) as f:
+        lines = f.readlines()
+    fn(lines)
+    with open(path, "w") as f:
+        f.writelines(lines)
+
+
+def p_onyxd_int(l):
+    i = find_one(l, "} VP8D_COMP;")
+    l.insert(i, "    void *b200_seam;   /* hostdec/vp8b200_seam.c state */\n")
+
+
+def p_decodframe(l):
+    i = find_one(l, '#include "onyxd_int.h"')
+    l.insert(i + 1, INC)
+    # S2: frame begin replaces the 127/129 edge setup (device applies the rule itself)
+    i = find_one(l, "vp8_setup_intra_recon(&pc->yv12_fb[pc->new_fb_idx]);")
+    l[i] = "        vp8b200_seam_frame_begin(pbi);\n"
+    # S3: per-MB record replaces prediction + residual
+    i = find_one(l, "/* do prediction */")
+    l.insert(i, "    vp8b200_seam_record_mb(pbi, xd, mb_idx);\n    return;\n")
+    # per-row 4-pixel extension: device rule, drop the host call (spans several lines)
+    i = find_one(l, "vp8_extend_mb_row(")
+    j = i
+    while ");" not in l[j]:
+        j += 1
+    l.insert(j + 1, "#endif\n")
+    l.insert(i, "#if 0 /* vp8b200: done on the device */\n")
+
+
+def p_onyxd_if(l):
+    i = find_one(l, '#include "onyxd_int.h"')
+    l.insert(i + 1, INC)
+    # S5: loop filter + border extension -> one asynchronous device submit
+    a = find_one(l, "if(cm->filter_level)")
+    b = find_one(l, "vp8_yv12_extend_frame_borders_ptr(cm->frame_to_show);")
+    assert a < b
+    l[a:b + 1] = ["        vp8b200_seam_frame_submit(pbi);\n"]
+    # get_raw_frame: refresh the host mirror of the shown buffer
+    i = find_one(l, "*sd = *pbi->common.frame_to_show;")
+    l.insert(i, "        vp8b200_seam_fetch(pbi);\n")
+    i = find_one(l, "vp8_remove_common(&pbi->common);")
+    l.insert(i, "    vp8b200_seam_destroy(pbi);\n")
+    # missing-frame path: device-side copy next to the host copy
+    i = find_one(l, "vp8_yv12_copy_frame_ptr(&cm->yv12_fb[prev_idx],")
+    j = i
+    while ");" not in l[j]:
+        j += 1
+    l.insert(j + 1, "            vp8b200_seam_copy_fb(pbi, cm->lst_fb_idx, prev_idx);\n")
+
+
+def p_yv12config(l):
+    i = find_one(l, '#include "vpx_mem/vpx_mem.h"')
+    l.insert(i + 1, INC)
+    i = find_one(l, "vpx_memalign(32, ybf->frame_size)")
+    l[i] = l[i].replace("vpx_memalign(32, ybf->frame_size)", "vp8b200_seam_alloc(ybf->frame_size)")
+    i = find_one(l, "vpx_free(ybf->buffer_alloc);")
+    l[i] = l[i].replace("vpx_free(ybf->buffer_alloc)", "vp8b200_seam_free(ybf->buffer_alloc)")
+
+
+def main():
+    ref, out = sys.argv[1], sys.argv[2]
+    if os.path.exists(out):
+        shutil.rmtree(out)
+    os.makedirs(out)
+    for item in COPY:
+        s, d = os.path.join(ref, item), os.path.join(out, item)
+        if os.path.isdir(s):
+            shutil.copytree(s, d)
+        else:
+            os.makedirs(os.path.dirname(d) or ".", exist_ok=True)
+            shutil.copy(s, d)
+    for root, _, files in os.walk(out):
+        os.chmod(root, 0o755)
+        for f in files:
+            os.chmod(os.path.join(root, f), 0o644)
+    patch(os.path.join(out, "vp8/decoder/onyxd_int.h"), p_onyxd_int)
+    patch(os.path.join(out, "vp8/decoder/decodframe.c"), p_decodframe)
+    patch(os.path.join(out, "vp8/decoder/onyxd_if.c"), p_onyxd_if)
+    patch(os.path.join(out, "vpx_scale/generic/yv12config.c"), p_yv12config)
+    print("apply_seams: patched host decoder in", out)
+
+
+if __name__ == "__main__":
+    main()

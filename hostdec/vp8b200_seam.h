@@ -1,0 +1,16 @@
+/* vp8b200_seam.h - prototypes of the seam functions called from the patched reference
+ * host decoder (see vp8b200_seam.c for the reference file:line of every call site). */
+#ifndef VP8B200_SEAM_H
+#define VP8B200_SEAM_H
+#include <stddef.h>
+struct VP8D_COMP;
+struct macroblockd;
+void *vp8b200_seam_alloc(size_t bytes);
+void  vp8b200_seam_free(void *p);
+void  vp8b200_seam_destroy(struct VP8D_COMP *pbi);
+void  vp8b200_seam_frame_begin(struct VP8D_COMP *pbi);
+void  vp8b200_seam_record_mb(struct VP8D_COMP *pbi, struct macroblockd *xd, unsigned int mb_idx);
+void  vp8b200_seam_frame_submit(struct VP8D_COMP *pbi);
+void  vp8b200_seam_fetch(struct VP8D_COMP *pbi);
+void  vp8b200_seam_copy_fb(struct VP8D_COMP *pbi, int dst_idx, int src_idx);
+#endif

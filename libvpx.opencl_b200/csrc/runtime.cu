@@ -1,0 +1,458 @@
+/* runtime.cu - contexts, device frame buffers, pinned staging ring, launch sequence and the
+ * C ABI of include/vp8b200.h.  No CPU reconstruction exists in this library: when CUDA is
+ * unavailable every entry point that would need the device fails.
+ *
+ * Per frame, on the context's stream:
+ *   H2D(records) -> k_inter -> k_intra -> k_loopfilter -> k_border     (-> D2H on fetch)
+ * which replaces, in the reference, decode_macroblock's tail (decodframe.c:190-304),
+ * vp8_loop_filter_frame (onyxd_if.c:576-586) and vp8_yv12_extend_frame_borders_ptr
+ * (onyxd_if.c:607).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+#include "vp8b200_internal.h"
+
+#define NSLOT 3          /* pinned/device record slots: parse N+1 while N uploads / runs */
+#define NBJOB 4          /* job-array ring for batched launches */
+
+struct Slot {
+    vp8b200_mb *h_mb, *d_mb;
+    vp8b200_aux *h_aux, *d_aux;
+    int16_t *h_coef, *d_coef;
+    FrameJob *h_job, *d_job;
+    cudaEvent_t h2d_done;
+    bool pending;
+};
+
+struct vp8b200_staged {
+    vp8b200_frame_hdr hdr;
+    uint8_t *d_blob;
+    vp8b200_mb *d_mb;
+    vp8b200_aux *d_aux;
+    int16_t *d_coef;
+    unsigned n_intra;
+};
+
+struct vp8b200_ctx {
+    int device;
+    Geo geo;
+    size_t frame_size;
+    int n_fb;
+    uint32_t n_mb;
+    uint8_t *fb[VP8B200_MAX_FB];
+    cudaStream_t stream;
+    Slot slot[NSLOT];
+    int cur;
+    bool open;
+    vp8b200_frame_hdr cur_hdr;
+    unsigned *d_progress;          /* 2*mb_rows wavefront counters */
+    unsigned *d_tickets;           /* [0] intra, [1] loop filter */
+    unsigned ticket_base[2];
+    unsigned epoch_intra, epoch_lf;
+    FrameJob *h_bjobs[NBJOB], *d_bjobs[NBJOB];
+    cudaEvent_t bjobs_done[NBJOB];
+    bool bjobs_pending[NBJOB];
+    int bjobs_cap, bjobs_cur;
+    uint64_t launches;
+    char err[256];
+};
+
+static const char *k_noerr = "";
+
+#define CK(ctx, call)                                                                      \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            snprintf((ctx)->err, sizeof((ctx)->err), "%s: %s", #call, cudaGetErrorString(e_)); \
+            return VP8B200_ERR_CUDA;                                                       \
+        }                                                                                  \
+    } while (0)
+
+extern "C" int vp8b200_abi_version(void) { return VP8B200_ABI_VERSION; }
+
+extern "C" const char *vp8b200_strerror(int st)
+{
+    switch (st) {
+    case VP8B200_OK: return "ok";
+    case VP8B200_ERR_INVALID: return "invalid argument or call order";
+    case VP8B200_ERR_NO_DEVICE: return "no usable CUDA device (this library has no CPU path)";
+    case VP8B200_ERR_NOMEM: return "out of memory";
+    case VP8B200_ERR_CUDA: return "CUDA error";
+    case VP8B200_ERR_OVERFLOW: return "record arena overflow";
+    default: return "unknown status";
+    }
+}
+
+extern "C" const char *vp8b200_last_error(const vp8b200_ctx *ctx) { return ctx ? ctx->err : k_noerr; }
+
+extern "C" int vp8b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" void *vp8b200_host_alloc(size_t bytes)
+{
+    void *p = NULL;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return NULL; }
+    return p;
+}
+extern "C" void vp8b200_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+static void free_ctx(vp8b200_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < c->n_fb; i++) cudaFree(c->fb[i]);
+    for (int i = 0; i < NSLOT; i++) {
+        Slot &s = c->slot[i];
+        cudaFreeHost(s.h_mb); cudaFreeHost(s.h_aux); cudaFreeHost(s.h_coef); cudaFreeHost(s.h_job);
+        cudaFree(s.d_mb); cudaFree(s.d_aux); cudaFree(s.d_coef); cudaFree(s.d_job);
+        if (s.h2d_done) cudaEventDestroy(s.h2d_done);
+    }
+    for (int i = 0; i < NBJOB; i++) {
+        cudaFreeHost(c->h_bjobs[i]); cudaFree(c->d_bjobs[i]);
+        if (c->bjobs_done[i]) cudaEventDestroy(c->bjobs_done[i]);
+    }
+    cudaFree(c->d_progress); cudaFree(c->d_tickets);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    cudaGetLastError();
+    delete c;
+}
+
+static int create_impl(vp8b200_ctx *c)
+{
+    const Geo &g = c->geo;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    vp8b200_upload_constants();
+    CK(c, cudaGetLastError());
+    for (int i = 0; i < c->n_fb; i++) {
+        CK(c, cudaMalloc((void **)&c->fb[i], c->frame_size));
+        CK(c, cudaMemsetAsync(c->fb[i], 0, c->frame_size, c->stream));
+    }
+    const size_t n_mb = c->n_mb;
+    for (int i = 0; i < NSLOT; i++) {
+        Slot &s = c->slot[i];
+        CK(c, cudaHostAlloc((void **)&s.h_mb, n_mb * sizeof(vp8b200_mb), cudaHostAllocPortable));
+        CK(c, cudaHostAlloc((void **)&s.h_aux, n_mb * sizeof(vp8b200_aux), cudaHostAllocPortable));
+        CK(c, cudaHostAlloc((void **)&s.h_coef, n_mb * 25 * 32, cudaHostAllocPortable));
+        CK(c, cudaHostAlloc((void **)&s.h_job, sizeof(FrameJob), cudaHostAllocPortable));
+        CK(c, cudaMalloc((void **)&s.d_mb, n_mb * sizeof(vp8b200_mb)));
+        CK(c, cudaMalloc((void **)&s.d_aux, n_mb * sizeof(vp8b200_aux)));
+        CK(c, cudaMalloc((void **)&s.d_coef, n_mb * 25 * 32));
+        CK(c, cudaMalloc((void **)&s.d_job, sizeof(FrameJob)));
+        CK(c, cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
+    }
+    for (int i = 0; i < NBJOB; i++) CK(c, cudaEventCreateWithFlags(&c->bjobs_done[i], cudaEventDisableTiming));
+    CK(c, cudaMalloc((void **)&c->d_progress, 2 * g.mb_rows * sizeof(unsigned)));
+    CK(c, cudaMemsetAsync(c->d_progress, 0, 2 * g.mb_rows * sizeof(unsigned), c->stream));
+    CK(c, cudaMalloc((void **)&c->d_tickets, 2 * sizeof(unsigned)));
+    CK(c, cudaMemsetAsync(c->d_tickets, 0, 2 * sizeof(unsigned), c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return VP8B200_OK;
+}
+
+extern "C" int vp8b200_create(vp8b200_ctx **out, int device, int width, int height, int n_fb)
+{
+    if (!out || width <= 0 || height <= 0 || (width & 15) || (height & 15) || width > 65536 ||
+        height > 65536 || n_fb < 1 || n_fb > VP8B200_MAX_FB)
+        return VP8B200_ERR_INVALID;
+    *out = NULL;
+    int ndev = vp8b200_device_count();
+    if (ndev <= 0 || device < 0 || device >= ndev) return VP8B200_ERR_NO_DEVICE;
+    vp8b200_ctx *c = new (std::nothrow) vp8b200_ctx();
+    if (!c) return VP8B200_ERR_NOMEM;
+    memset(c, 0, sizeof *c);
+    c->device = device;
+    c->n_fb = n_fb;
+    Geo &g = c->geo;
+    g.width = width; g.height = height;
+    g.mb_cols = width >> 4; g.mb_rows = height >> 4;
+    g.y_stride = ((width + 2 * VP8B200_BORDER) + 31) & ~31;          /* yv12config.c:61 */
+    g.uv_stride = g.y_stride >> 1;
+    const size_t yplane = (size_t)(height + 2 * VP8B200_BORDER) * g.y_stride;
+    g.uv_rows_alloc = (height >> 1) + VP8B200_BORDER;
+    const size_t uvplane = (size_t)g.uv_rows_alloc * g.uv_stride;
+    c->frame_size = yplane + 2 * uvplane;
+    g.y_off = VP8B200_BORDER * g.y_stride + VP8B200_BORDER;          /* yv12config.c:107-109 */
+    g.u_off = (int)yplane + (VP8B200_BORDER / 2) * g.uv_stride + VP8B200_BORDER / 2;
+    g.v_off = (int)(yplane + uvplane) + (VP8B200_BORDER / 2) * g.uv_stride + VP8B200_BORDER / 2;
+    c->n_mb = (uint32_t)(g.mb_cols * g.mb_rows);
+    c->epoch_intra = c->epoch_lf = 0;
+    int st = create_impl(c);
+    if (st != VP8B200_OK) {
+        fprintf(stderr, "vp8b200_create: %s\n", c->err);
+        free_ctx(c);
+        return st;
+    }
+    *out = c;
+    return VP8B200_OK;
+}
+
+extern "C" void vp8b200_destroy(vp8b200_ctx *ctx) { free_ctx(ctx); }
+extern "C" size_t vp8b200_frame_size(const vp8b200_ctx *ctx) { return ctx ? ctx->frame_size : 0; }
+extern "C" int vp8b200_y_stride(const vp8b200_ctx *ctx) { return ctx ? ctx->geo.y_stride : 0; }
+extern "C" uint64_t vp8b200_launch_count(const vp8b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void *vp8b200_stream(const vp8b200_ctx *ctx) { return ctx ? (void *)ctx->stream : NULL; }
+
+static bool hdr_ok(const vp8b200_ctx *c, const vp8b200_frame_hdr *h)
+{
+    return h->fb_new < c->n_fb && h->fb_last < c->n_fb && h->fb_golden < c->n_fb &&
+           h->fb_altref < c->n_fb && h->frame_type <= 1 && h->filter_level <= 63 &&
+           h->sharpness_level <= 7;
+}
+
+extern "C" int vp8b200_frame_begin(vp8b200_ctx *c, const vp8b200_frame_hdr *hdr, vp8b200_frame_bufs *bufs)
+{
+    if (!c || !hdr || !bufs || !hdr_ok(c, hdr)) return VP8B200_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    c->open = false;
+    Slot &s = c->slot[c->cur];
+    if (s.pending) {                         /* the upload that last used this slot */
+        CK(c, cudaEventSynchronize(s.h2d_done));
+        s.pending = false;
+    }
+    c->cur_hdr = *hdr;
+    bufs->mb = s.h_mb; bufs->aux = s.h_aux; bufs->coef = s.h_coef;
+    bufs->aux_capacity = c->n_mb; bufs->coef_capacity = c->n_mb * 25;
+    c->open = true;
+    return VP8B200_OK;
+}
+
+extern "C" int vp8b200_frame_abort(vp8b200_ctx *c)
+{
+    if (!c) return VP8B200_ERR_INVALID;
+    c->open = false;
+    return VP8B200_OK;
+}
+
+static unsigned count_intra(const vp8b200_mb *mb, uint32_t n)
+{
+    unsigned k = 0;
+    for (uint32_t i = 0; i < n; i++) k += mb[i].ref_frame == VP8B200_INTRA_FRAME;
+    return k;
+}
+
+/* validate what the kernels will index with (a corrupt record must not become a wild read) */
+static bool records_ok(const Geo &g, const vp8b200_mb *mb, const vp8b200_aux *aux, uint32_t n_mb,
+                       uint32_t n_aux, uint32_t n_coef, bool key)
+{
+    for (uint32_t i = 0; i < n_mb; i++) {
+        const vp8b200_mb &m = mb[i];
+        if (m.y_mode > VP8B200_SPLITMV || m.uv_mode > VP8B200_TM_PRED || m.ref_frame > 3) return false;
+        bool intra = m.ref_frame == VP8B200_INTRA_FRAME;
+        if (intra != (m.y_mode <= VP8B200_B_PRED)) return false;
+        if (key && !intra) return false;
+        if ((m.y_mode == VP8B200_B_PRED || m.y_mode == VP8B200_SPLITMV) && m.u.aux >= n_aux) return false;
+        if (!intra && !(m.flags & VP8B200_MBF_CLAMP_MVS)) {
+            /* an unclamped MV must already be inside the range clamp_mv_to_umv_border
+             * (reconinter.c:348-368) leaves alone, or the 32-pixel border would not cover
+             * the filter window */
+            const int row = (int)(i / (uint32_t)g.mb_cols), col = (int)(i % (uint32_t)g.mb_cols);
+            const int lo_c = -((col * 16) << 3) - (19 << 3), hi_c = (((g.mb_cols - 1 - col) * 16) << 3) + (18 << 3);
+            const int lo_r = -((row * 16) << 3) - (19 << 3), hi_r = (((g.mb_rows - 1 - row) * 16) << 3) + (18 << 3);
+            const int nmv = m.y_mode == VP8B200_SPLITMV ? 16 : 1;
+            for (int k = 0; k < nmv; k++) {
+                int r = nmv == 1 ? m.u.mv.row : aux[m.u.aux].mv[k].row;
+                int c = nmv == 1 ? m.u.mv.col : aux[m.u.aux].mv[k].col;
+                if (r < lo_r || r > hi_r || c < lo_c || c > hi_c) return false;
+            }
+        }
+        if (m.coef_mask >> 25) return false;
+        if (m.coef_mask && (uint64_t)m.coef_off + (unsigned)__builtin_popcount(m.coef_mask) > n_coef) return false;
+    }
+    return true;
+}
+
+static void fill_job(vp8b200_ctx *c, FrameJob *j, const vp8b200_frame_hdr &h, const vp8b200_mb *d_mb,
+                     const vp8b200_aux *d_aux, const int16_t *d_coef, unsigned n_intra,
+                     bool run_intra, bool run_lf)
+{
+    memset(j, 0, sizeof *j);
+    j->dst = c->fb[h.fb_new];
+    j->ref[1] = c->fb[h.fb_last]; j->ref[2] = c->fb[h.fb_golden]; j->ref[3] = c->fb[h.fb_altref];
+    j->mb = d_mb; j->aux = d_aux; j->coef = d_coef;
+    j->progress = c->d_progress;
+    if (run_intra) c->epoch_intra++;
+    if (run_lf) c->epoch_lf++;
+    j->epoch_intra = c->epoch_intra;
+    j->epoch_lf = c->epoch_lf;
+    j->n_intra = n_intra;
+    j->hdr = h;
+}
+
+/* the launch sequence shared by frame_submit (n = 1) and batch_run */
+static int run_jobs(vp8b200_ctx *c, const FrameJob *d_jobs, int n, bool any_inter, bool any_intra, bool any_lf)
+{
+    int nctas = 0;
+    if (any_inter) { vp8b200_launch_inter(c->stream, d_jobs, n, c->geo); c->launches++; }
+    if (any_intra) {
+        vp8b200_launch_intra(c->stream, d_jobs, n, c->geo, c->d_tickets + 0, c->ticket_base[0], &nctas);
+        c->ticket_base[0] += (unsigned)nctas; c->launches++;
+    }
+    if (any_lf) {
+        vp8b200_launch_loopfilter(c->stream, d_jobs, n, c->geo, c->d_tickets + 1, c->ticket_base[1], &nctas);
+        c->ticket_base[1] += (unsigned)nctas; c->launches++;
+    }
+    vp8b200_launch_border(c->stream, d_jobs, n, c->geo);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return VP8B200_OK;
+}
+
+extern "C" int vp8b200_frame_submit(vp8b200_ctx *c, uint32_t n_aux, uint32_t n_coef)
+{
+    if (!c || !c->open) return VP8B200_ERR_INVALID;
+    c->open = false;
+    if (n_aux > c->n_mb || n_coef > c->n_mb * 25) return VP8B200_ERR_OVERFLOW;
+    CK(c, cudaSetDevice(c->device));
+    Slot &s = c->slot[c->cur];
+    const vp8b200_frame_hdr &h = c->cur_hdr;
+    const bool key = h.frame_type == 0;
+    if (!records_ok(c->geo, s.h_mb, s.h_aux, c->n_mb, n_aux, n_coef, key)) {
+        snprintf(c->err, sizeof c->err, "macroblock records failed validation");
+        return VP8B200_ERR_INVALID;
+    }
+    const unsigned n_intra = count_intra(s.h_mb, c->n_mb);
+    const bool run_intra = n_intra > 0, run_lf = h.filter_level != 0;
+    fill_job(c, s.h_job, h, s.d_mb, s.d_aux, s.d_coef, n_intra, run_intra, run_lf);
+    CK(c, cudaMemcpyAsync(s.d_mb, s.h_mb, (size_t)c->n_mb * sizeof(vp8b200_mb), cudaMemcpyHostToDevice, c->stream));
+    if (n_aux) CK(c, cudaMemcpyAsync(s.d_aux, s.h_aux, (size_t)n_aux * sizeof(vp8b200_aux), cudaMemcpyHostToDevice, c->stream));
+    if (n_coef) CK(c, cudaMemcpyAsync(s.d_coef, s.h_coef, (size_t)n_coef * 32, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(s.d_job, s.h_job, sizeof(FrameJob), cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaEventRecord(s.h2d_done, c->stream));
+    s.pending = true;
+    int st = run_jobs(c, s.d_job, 1, !key, run_intra, run_lf);
+    c->cur = (c->cur + 1) % NSLOT;
+    return st;
+}
+
+extern "C" int vp8b200_frame_fetch(vp8b200_ctx *c, int fb, uint8_t *dst, size_t bytes)
+{
+    if (!c || fb < 0 || fb >= c->n_fb || !dst || bytes > c->frame_size) return VP8B200_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaMemcpyAsync(dst, c->fb[fb], bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return VP8B200_OK;
+}
+
+extern "C" int vp8b200_frame_upload(vp8b200_ctx *c, int fb, const uint8_t *src, size_t bytes)
+{
+    if (!c || fb < 0 || fb >= c->n_fb || !src || bytes > c->frame_size) return VP8B200_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaMemcpyAsync(c->fb[fb], src, bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return VP8B200_OK;
+}
+
+extern "C" int vp8b200_frame_copy(vp8b200_ctx *c, int fb_dst, int fb_src)
+{
+    if (!c || fb_dst < 0 || fb_dst >= c->n_fb || fb_src < 0 || fb_src >= c->n_fb) return VP8B200_ERR_INVALID;
+    if (fb_dst == fb_src) return VP8B200_OK;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaMemcpyAsync(c->fb[fb_dst], c->fb[fb_src], c->frame_size, cudaMemcpyDeviceToDevice, c->stream));
+    return VP8B200_OK;
+}
+
+extern "C" int vp8b200_sync(vp8b200_ctx *c)
+{
+    if (!c) return VP8B200_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return VP8B200_OK;
+}
+
+/* ---- resident frames and batched replay ------------------------------------------------- */
+
+extern "C" int vp8b200_stage_frame(vp8b200_ctx *c, const vp8b200_frame_hdr *hdr, const vp8b200_mb *mb,
+                                   const vp8b200_aux *aux, uint32_t n_aux, const int16_t *coef,
+                                   uint32_t n_coef, vp8b200_staged **out)
+{
+    if (!c || !hdr || !mb || !out || !hdr_ok(c, hdr) || (n_aux && !aux) || (n_coef && !coef))
+        return VP8B200_ERR_INVALID;
+    if (n_aux > c->n_mb || n_coef > c->n_mb * 25) return VP8B200_ERR_OVERFLOW;
+    if (!records_ok(c->geo, mb, aux, c->n_mb, n_aux, n_coef, hdr->frame_type == 0)) {
+        snprintf(c->err, sizeof c->err, "macroblock records failed validation");
+        return VP8B200_ERR_INVALID;
+    }
+    CK(c, cudaSetDevice(c->device));
+    vp8b200_staged *s = new (std::nothrow) vp8b200_staged();
+    if (!s) return VP8B200_ERR_NOMEM;
+    const size_t mb_b = (size_t)c->n_mb * sizeof(vp8b200_mb);
+    const size_t aux_b = ((size_t)n_aux * sizeof(vp8b200_aux) + 255) & ~(size_t)255;
+    const size_t coef_b = (size_t)n_coef * 32;
+    const size_t mb_pad = (mb_b + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc((void **)&s->d_blob, mb_pad + aux_b + coef_b + 256);
+    if (e != cudaSuccess) {
+        snprintf(c->err, sizeof c->err, "cudaMalloc(staged): %s", cudaGetErrorString(e));
+        delete s;
+        return VP8B200_ERR_CUDA;
+    }
+    s->hdr = *hdr;
+    s->d_mb = (vp8b200_mb *)s->d_blob;
+    s->d_aux = (vp8b200_aux *)(s->d_blob + mb_pad);
+    s->d_coef = (int16_t *)(s->d_blob + mb_pad + aux_b);
+    s->n_intra = count_intra(mb, c->n_mb);
+    /* staging is a setup-time operation: plain synchronous copies from pageable memory */
+    CK(c, cudaMemcpy(s->d_mb, mb, mb_b, cudaMemcpyHostToDevice));
+    if (n_aux) CK(c, cudaMemcpy(s->d_aux, aux, (size_t)n_aux * sizeof(vp8b200_aux), cudaMemcpyHostToDevice));
+    if (n_coef) CK(c, cudaMemcpy(s->d_coef, coef, coef_b, cudaMemcpyHostToDevice));
+    *out = s;
+    return VP8B200_OK;
+}
+
+extern "C" void vp8b200_staged_free(vp8b200_ctx *c, vp8b200_staged *s)
+{
+    if (!s) return;
+    if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+    cudaFree(s->d_blob);
+    delete s;
+}
+
+extern "C" int vp8b200_batch_run(vp8b200_ctx *const *ctx, vp8b200_staged *const *frame, int n)
+{
+    if (!ctx || !frame || n < 1 || !ctx[0]) return VP8B200_ERR_INVALID;
+    vp8b200_ctx *c = ctx[0];
+    for (int i = 0; i < n; i++) {
+        if (!ctx[i] || !frame[i] || ctx[i]->device != c->device ||
+            ctx[i]->geo.width != c->geo.width || ctx[i]->geo.height != c->geo.height)
+            return VP8B200_ERR_INVALID;
+        for (int k = 0; k < i; k++) if (ctx[k] == ctx[i]) return VP8B200_ERR_INVALID;
+    }
+    CK(c, cudaSetDevice(c->device));
+    if (n > c->bjobs_cap) {
+        CK(c, cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < NBJOB; i++) {
+            cudaFreeHost(c->h_bjobs[i]); cudaFree(c->d_bjobs[i]);
+            c->h_bjobs[i] = NULL; c->d_bjobs[i] = NULL; c->bjobs_pending[i] = false;
+            CK(c, cudaHostAlloc((void **)&c->h_bjobs[i], (size_t)n * sizeof(FrameJob), cudaHostAllocPortable));
+            CK(c, cudaMalloc((void **)&c->d_bjobs[i], (size_t)n * sizeof(FrameJob)));
+        }
+        c->bjobs_cap = n;
+    }
+    const int r = c->bjobs_cur;
+    if (c->bjobs_pending[r]) { CK(c, cudaEventSynchronize(c->bjobs_done[r])); c->bjobs_pending[r] = false; }
+    bool any_inter = false, any_intra = false, any_lf = false;
+    for (int i = 0; i < n; i++) {
+        const vp8b200_staged *s = frame[i];
+        const bool run_intra = s->n_intra > 0, run_lf = s->hdr.filter_level != 0;
+        any_inter |= s->hdr.frame_type != 0; any_intra |= run_intra; any_lf |= run_lf;
+    }
+    for (int i = 0; i < n; i++) {
+        const vp8b200_staged *s = frame[i];
+        /* every job of a launched wavefront kernel publishes progress, so every context's
+         * epoch advances with the launch, not with its own need for the kernel */
+        fill_job(ctx[i], &c->h_bjobs[r][i], s->hdr, s->d_mb, s->d_aux, s->d_coef, s->n_intra,
+                 any_intra, any_lf && s->hdr.filter_level != 0);
+    }
+    CK(c, cudaMemcpyAsync(c->d_bjobs[r], c->h_bjobs[r], (size_t)n * sizeof(FrameJob), cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaEventRecord(c->bjobs_done[r], c->stream));
+    c->bjobs_pending[r] = true;
+    c->bjobs_cur = (r + 1) % NBJOB;
+    return run_jobs(c, c->d_bjobs[r], n, any_inter, any_intra, any_lf);
+}

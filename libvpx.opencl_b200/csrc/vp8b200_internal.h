@@ -1,0 +1,46 @@
+/* vp8b200_internal.h - shared between the runtime (runtime.cu) and the kernels. */
+#ifndef VP8B200_INTERNAL_H
+#define VP8B200_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "vp8b200.h"
+
+/* Frame-buffer geometry: the reference's YV12 layout (vpx_scale/generic/yv12config.c:55-110),
+ * identical for every job of a batched launch. */
+struct Geo {
+    int mb_cols, mb_rows;
+    int width, height;          /* coded luma size */
+    int y_stride, uv_stride;
+    int y_off, u_off, v_off;    /* byte offset of pixel (0,0) of each plane in the allocation */
+    int uv_rows_alloc;          /* height/2 + 32 */
+};
+
+/* One frame of one stream, as the kernels see it (lives in device memory). */
+struct FrameJob {
+    uint8_t *dst;                 /* buffer being reconstructed (hdr.fb_new)                  */
+    const uint8_t *ref[4];        /* [1] last, [2] golden, [3] altref; [0] unused             */
+    const vp8b200_mb *mb;
+    const vp8b200_aux *aux;
+    const int16_t *coef;
+    unsigned int *progress;       /* [0,mb_rows): intra wavefront, [mb_rows,2*mb_rows): LF    */
+    unsigned int epoch_intra;     /* progress values of this frame are (epoch << 13) + columns; */
+    unsigned int epoch_lf;        /* each counter advances only when its kernel really runs     */
+    unsigned int n_intra;         /* intra macroblocks in the frame (0 => intra kernel idle)  */
+    vp8b200_frame_hdr hdr;
+};
+
+#define VP8B200_EPOCH_SHIFT 13    /* mb_cols <= 4096 < 2^13 */
+
+void vp8b200_upload_constants();   /* filter taps -> __constant__ on the current device */
+
+/* launch wrappers (kernels_*.cu); `tickets` points at two device counters owned by the
+ * launching context, ticket_base = value of the counter before this launch */
+void vp8b200_launch_inter(cudaStream_t s, const FrameJob *jobs, int n_jobs, const Geo &g);
+void vp8b200_launch_intra(cudaStream_t s, const FrameJob *jobs, int n_jobs, const Geo &g,
+                          unsigned int *ticket, unsigned int ticket_base, int *n_ctas);
+void vp8b200_launch_loopfilter(cudaStream_t s, const FrameJob *jobs, int n_jobs, const Geo &g,
+                               unsigned int *ticket, unsigned int ticket_base, int *n_ctas);
+void vp8b200_launch_border(cudaStream_t s, const FrameJob *jobs, int n_jobs, const Geo &g);
+
+#endif

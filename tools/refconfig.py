@@ -1,14 +1,15 @@
 #!/usr/bin/env python3
 """Write the three configuration headers the reference sources expect.
 
-TEST INFRASTRUCTURE ONLY (see oracle/README.md).  The reference tree ships no
+Build tool shared by oracle/refbuild (the unmodified reference = the checker) and
+hostdec (the reference's host parser with the B200 seams).  The reference tree ships no
 pre-generated vpx_config.h / vpx_rtcd.h / vpx_version.h: its own configure +
 rtcd.sh produce them.  We do not run that build system; this script writes the
 equivalent of a `--target=generic-gnu --disable-multithread` configuration
 (every RTCD name bound to its `_c` implementation) so that
 `oracle/refbuild/Makefile` can compile the reference sources where they lie.
 
-usage: gen_config.py <reference_root> <out_dir>
+usage: refconfig.py <reference_root> <out_dir> [KEY=VALUE ...]   (overrides, e.g. CONFIG_B200=1)
 Outputs: <out_dir>/vpx_config.h, vpx_rtcd.h, vpx_version.h, vpx_config.c
 """
 import os
@@ -97,6 +98,9 @@ def gen_rtcd(defs_path):
 
 def main():
     ref, outdir = sys.argv[1], sys.argv[2]
+    for kv in sys.argv[3:]:
+        k, v = kv.split("=")
+        CONFIG[k] = int(v)
     os.makedirs(outdir, exist_ok=True)
     # vpx_scale/yv12config.h includes "../vpx_config.h": the Makefile passes
     # -I<out_dir>/inc so that "<out_dir>/inc/../vpx_config.h" resolves here.
