@@ -1,0 +1,340 @@
+#!/usr/bin/env python3
+"""bench.py - VP8 decode throughput of the B200 reconstruction path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            (our arm)
+  python bench.py --impl reference --gpus N --steps K ...  (reference CPU decoder, rank 0)
+
+Workload (config.workload = "c5_64x1080p"): BASELINE.json configs[4] - 64 independent
+1080p profile-0 streams (six-tap MC, normal loop filter; synthetic translated texture, encoded
+by the reference's vpxenc) per GPU; ranks take whole streams (weak scaling, no collective).
+A "step" = one frame of every stream of the rank (64 frames) reconstructed by ONE batched
+launch of each kernel.
+
+  value : frames/s with the per-frame macroblock records already resident in HBM
+          (vp8b200_stage_frame + vp8b200_batch_run), CUDA events on the launching stream.
+          Per step the kernels touch ~0.5 GB (64 frames x (reference + destination + records)),
+          far more than the 126 MB L2, so no L2 flush is needed between steps.
+  e2e   : frames/s through the reference's public API (vpx_codec_decode / vpx_codec_get_frame,
+          hostdec/b200bench) from IVF bytes in host memory to vpx_image_t in host memory:
+          host entropy decode + H2D of the records + kernels + D2H of every frame.
+  roofline     : the loop-filter kernel (dominant), algorithmic bytes / CUDA-event time.
+  cpu_baseline : the unmodified reference decoder (oracle/_ref) on the host cores, bounded sample.
+"""
+import argparse
+import glob
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "libvpx.opencl_b200"))
+
+STREAMS = os.path.join(ROOT, "streams")
+HOSTDEC = os.path.join(ROOT, "hostdec", "_build")
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+METRIC = "decode_fps_1080p_64streams_md5_exact"
+
+
+def find_clips():
+    clips = sorted(glob.glob(os.path.join(STREAMS, "c5_1080p_s*.ivf")))
+    if not clips:
+        raise SystemExit("bench: no streams/c5_1080p_s*.ivf - run tools/make_streams.py in the build container")
+    return clips
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.p = gpu, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": reasons}
+
+
+def capture_records(clips, tmpdir):
+    """Untimed setup: run the host parser in record-capture mode over each clip (no pixels are
+    produced in this mode; it only yields the exact C-ABI input of every frame)."""
+    procs = []
+    for i, c in enumerate(clips):
+        out = os.path.join(tmpdir, "clip%03d.rec" % i)
+        env = dict(os.environ, VP8B200_NO_DEVICE="1", VP8B200_DUMP=out)
+        procs.append((out, subprocess.Popen([os.path.join(HOSTDEC, "vpxdec_b200"), "--noblit", c], env=env,
+                                            stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)))
+        if len(procs) % (os.cpu_count() or 8) == 0:
+            for _, p in procs:
+                p.wait()
+    outs = []
+    for out, p in procs:
+        if p.wait() != 0:
+            raise SystemExit("bench: record capture failed for " + out)
+        outs.append(out)
+    return outs
+
+
+def frame_bytes_model(fr, na):
+    """Algorithmic bytes per frame and kernel (DESIGN.md section 5 / SURVEY.md 8d)."""
+    lvl, simple, key = int(fr.hdr["filter_level"]), int(fr.hdr["filter_type"]) != 0, int(fr.hdr["frame_type"]) == 0
+    rec = 16 * fr.mb.shape[0] + 64 * fr.n_aux + 32 * fr.n_coef
+    lf = 0 if lvl == 0 else (2 * na if simple else 3 * na)
+    pred = 1.5 * na + rec + (0 if key else 1.5 * na)
+    return {"loopfilter": lf, "pred": pred}
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    from vp8b200 import abi, recfile, frames, shard
+
+    rank, local_rank, world = shard.rank_info()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    clips = find_clips()
+    S = args.streams
+    mine = shard.streams_for_rank(rank, S, len(clips))
+    uniq = sorted(set(mine))
+    md5s = {u: open(clips[u][:-4] + ".md5").read().split() for u in uniq}
+
+    # ---- setup (untimed): records of every clip this rank plays, staged in HBM -------------
+    t_setup = time.time()
+    with tempfile.TemporaryDirectory() as tmp:
+        recs = {}
+        for u, path in zip(uniq, capture_records([clips[u] for u in uniq], tmp)):
+            recs[u] = recfile.read(path)
+            os.unlink(path)
+    r0 = recs[uniq[0]]
+    F = min(len(r.frames) for r in recs.values())
+    geo = frames.Geometry(r0.coded_width, r0.coded_height)
+    na = r0.coded_width * r0.coded_height
+    ctxs = [abi.Context(r0.coded_width, r0.coded_height, r0.n_fb, device=local_rank) for _ in range(S)]
+    staged_u = {u: [ctxs[0].stage(fr) for fr in recs[u].frames[:F]] for u in uniq}   # shared device blobs
+    staged = [[staged_u[mine[s]][f] for s in range(S)] for f in range(F)]
+    stream = torch.cuda.ExternalStream(ctxs[0].stream(), device=dev)
+    t_setup = time.time() - t_setup
+
+    def step(i):
+        abi.batch_run(ctxs, staged[i % F])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: HBM-resident replay ---------------------------------------------------------
+    W, K = args.warmup, args.steps
+    for i in range(W):
+        step(i)
+    first = W % F and (F - W % F) or 0          # continue the clip so every timed step has its reference
+    for i in range(W, W + first):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctxs[0].launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(K):
+        step(i)
+    e1.record(stream)
+    ctxs[0].sync()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = ctxs[0].launch_count() - l0
+    tot_frames, tot_s = shard.combine(dist, dev, K * S, ms / 1e3)
+    value = tot_frames / tot_s
+
+    # ---- parity (untimed): one clean pass, per-frame MD5 of fetched frames vs the reference --
+    checked = 0
+    check_streams = list(range(0, S, max(1, S // 4)))[:4]
+    for f in range(0 if not args.skip_verify else F, F):
+        step(f)
+        for s in check_streams:
+            fr = recs[mine[s]].frames[f]
+            if fr.show_frame:
+                got = frames.md5_hex(geo.i420(ctxs[s].fetch(int(fr.fb_show)), r0.display_width, r0.display_height))
+                if got != md5s[mine[s]][f]:
+                    raise SystemExit("bench: MD5 mismatch stream %d frame %d - result invalid" % (s, f))
+                checked += 1
+
+    # ---- per-kernel device time (events around each launch; separate pass) -------------------
+    ctxs[0].profile(True)
+    for f in range(F):
+        step(f)
+    prof = ctxs[0].profile_read()
+    ctxs[0].profile(False)
+    lf_bytes = sum(frame_bytes_model(recs[mine[s]].frames[f], na)["loopfilter"] for f in range(F) for s in range(S))
+    pred_bytes = sum(frame_bytes_model(recs[mine[s]].frames[f], na)["pred"] for f in range(F) for s in range(S))
+    peak, peak_src = measured_peak()
+    lf_ms, lf_n = prof["loopfilter"]
+    kern = {k: {"ms_total": round(v[0], 3), "launches": v[1]} for k, v in prof.items()}
+    tot_ms = sum(v[0] for v in prof.values()) or 1.0
+    for k in kern:
+        kern[k]["share"] = round(prof[k][0] / tot_ms, 4)
+    pred_ms = prof["inter"][0] + prof["intra"][0]
+    kern["pred_GBps"] = round(pred_bytes / (pred_ms / 1e3) / 1e9, 1) if pred_ms else None
+    achieved = lf_bytes / (lf_ms / 1e3) / 1e9 if lf_ms else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_loopfilter", "achieved": round(achieved, 1), "peak": peak,
+                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                "peak_source": peak_src, "bytes_per_launch": round(lf_bytes / max(lf_n, 1)),
+                "ms_per_launch": round(lf_ms / max(lf_n, 1), 4), "kernels": kern}
+
+    for c in ctxs[1:]:
+        c.close()
+    ctxs[0].close()
+
+    # ---- e2e: public API, host buffers in, host frames out -----------------------------------
+    e2e = None if args.skip_e2e else run_e2e(args, clips, mine, local_rank, dist, dev, shard, S)
+
+    # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = run_refbench(clips, sample_streams=min(len(clips), os.cpu_count() or 1), repeat=1)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": round(tot_s * 1e3 / K, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "c5_64x1080p", "streams_per_gpu": S, "frames_per_clip": F,
+                       "unique_clips": len(clips), "resolution": "1920x1080 (coded 1920x1088)",
+                       "profile": 0, "loop_filter": "normal", "mc": "sixtap",
+                       "step": "one frame of each of the %d streams (one batched launch per kernel)" % S,
+                       "l2_policy": "inputs per step (~%.0f MB) exceed the 126 MB L2" % (S * 3 * geo.frame_size / 1e6),
+                       "pixels_per_s": round(value * 1920 * 1080), "md5_checked_frames": checked,
+                       "setup_s": round(t_setup, 1)},
+            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, clips, mine, local_rank, dist, dev, shard, S):
+    threads = args.e2e_threads or S
+    repeat = max(1, args.e2e_repeat)
+    env = dict(os.environ, VP8B200_DEVICE=str(local_rank), VP8B200_SYNC="block")
+    cmd = [os.path.join(HOSTDEC, "b200bench"), "--threads", str(threads), "--streams", str(S),
+           "--repeat", str(repeat)] + [clips[u] for u in mine]
+    if dist is not None:
+        dist.barrier()
+    out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    if out.returncode != 0:
+        raise SystemExit("bench: b200bench failed: " + out.stderr[-400:])
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    frames_tot, wall = shard.combine(dist, dev, r["frames"], r["wall_s"])
+    per_step = S / max(r["frames"], 1)
+    return {"value": round(frames_tot / wall, 2), "unit": "frames/s",
+            "h2d_bytes_per_step": round(r["h2d_bytes"] * per_step), "d2h_bytes_per_step": round(r["d2h_bytes"] * per_step),
+            "api": "vpx_codec_decode/vpx_codec_get_frame (hostdec/b200bench)", "host_threads": r["threads"],
+            "host_cores": os.cpu_count(), "frames": r["frames"], "wall_s": round(r["wall_s"], 3)}
+
+
+def run_refbench(clips, sample_streams, repeat, procs=None):
+    procs = procs or os.cpu_count() or 1
+    cmd = [os.path.join(REFDIR, "refbench"), "--procs", str(procs), "--repeat", str(repeat), "--touch"] + clips[:sample_streams]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    if out.returncode != 0:
+        raise SystemExit("bench: refbench failed: " + out.stderr[-400:])
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    return {"value": round(r["fps"], 2), "unit": "frames/s", "cores": r["procs"], "kind": "reference",
+            "sample": "%d 1080p clips x %d pass(es) = %d frames, unmodified reference generic-C decoder, "
+                      "one process per core" % (sample_streams, repeat, r["frames"]),
+            "wall_s": round(r["wall_s"], 3)}
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path, all host cores, same config/metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    clips = find_clips()
+    S = args.streams
+    use = [clips[i % len(clips)] for i in range(S)]
+    # K steps = K frames of each of the S streams; the clip has F frames -> ceil(K/F) passes
+    F = len(open(use[0][:-4] + ".md5").read().split())
+    passes = max(1, -(-args.steps // F))
+    procs = os.cpu_count() or 1
+    cmd = [os.path.join(REFDIR, "refbench"), "--procs", str(procs), "--repeat", str(passes), "--touch"] + use
+    if args.warmup:
+        subprocess.run([os.path.join(REFDIR, "refbench"), "--procs", str(procs)] + use[:procs], stdout=subprocess.DEVNULL)
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    if out.returncode != 0:
+        raise SystemExit("bench: refbench failed: " + out.stderr[-400:])
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    steps = r["frames"] / S
+    cpu = {"value": round(r["fps"], 2), "unit": "frames/s", "cores": r["procs"], "kind": "reference",
+           "sample": "%d streams x %d pass(es) of %d frames, one process per core" % (S, passes, F)}
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(r["fps"], 2), "unit": "frames/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": int(steps), "warmup": args.warmup,
+        "ms_per_step": round(r["wall_s"] * 1e3 / steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "c5_64x1080p", "streams_per_gpu": S, "frames_per_clip": F,
+                   "note": "CPU only: host cores do not scale with --gpus; rank 0 runs, others idle"},
+        "cpu_baseline": cpu,
+        "e2e": {"value": round(r["fps"], 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=90)
+    ap.add_argument("--warmup", type=int, default=30)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=64, help="independent streams per GPU")
+    ap.add_argument("--e2e-threads", type=int, default=0)
+    ap.add_argument("--e2e-repeat", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: kernels only")
+    ap.add_argument("--skip-verify", action="store_true", help="profiling runs: no MD5 pass")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -1,0 +1,178 @@
+/* b200bench - multi-stream end-to-end driver over the reference's PUBLIC decoder API
+ * (vpx_codec_dec_init / vpx_codec_decode / vpx_codec_get_frame, reference
+ * vpx/vpx_decoder.h; call order of vpxdec.c:985-1067), linked against the host decoder with
+ * the B200 seams (libvpx_b200.so).  Input: IVF files in host memory; output: vpx_image_t in
+ * host memory.  So every timed frame pays host parse + H2D of the records + device
+ * reconstruction + D2H of the frame - this is bench.py's "e2e" figure.
+ *
+ * S decoder instances (instance i plays file i % nfiles), T worker threads (thread t owns
+ * instances t, t+T, ...; it advances them round-robin one frame at a time).  Each worker
+ * first creates its decoders and decodes one warm-up pass (device allocations, clocks),
+ * then all workers meet at a barrier and decode `repeat` timed passes of their clips.
+ *
+ * usage: b200bench [--threads T] [--streams S] [--repeat R] [--sum] a.ivf [b.ivf ...]
+ *   --sum : print a byte-sum of every visible frame of instance 0's last pass (cheap check
+ *           that pixels really arrive in host memory)
+ * prints one JSON line.
+ */
+#define _GNU_SOURCE
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include "vpx/vpx_decoder.h"
+#include "vpx/vp8dx.h"
+#include "vp8b200.h"
+
+typedef struct { uint8_t *data; size_t size; int nframes; size_t *off; uint32_t *len; } clip_t;
+typedef struct { vpx_codec_ctx_t dec; const clip_t *clip; int ready; } inst_t;
+
+static int g_threads = 1, g_streams = 1, g_repeat = 1, g_sum = 0, g_nclips = 0;
+static clip_t g_clips[1024];
+static inst_t *g_inst;
+static pthread_barrier_t g_bar;
+static double g_t0, g_t1[1024];
+static long g_frames[1024];
+static uint64_t g_checksum;
+
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+static void load_clip(clip_t *c, const char *path)
+{
+    FILE *f = fopen(path, "rb");
+    size_t pos = 32;
+    int cap = 1024;
+    if (!f) { perror(path); exit(2); }
+    fseek(f, 0, SEEK_END); c->size = (size_t)ftell(f); fseek(f, 0, SEEK_SET);
+    c->data = (uint8_t *)malloc(c->size);
+    if (fread(c->data, 1, c->size, f) != c->size) { perror("fread"); exit(2); }
+    fclose(f);
+    if (c->size < 32 || memcmp(c->data, "DKIF", 4)) { fprintf(stderr, "%s: not IVF\n", path); exit(2); }
+    c->off = (size_t *)malloc(sizeof(size_t) * cap);
+    c->len = (uint32_t *)malloc(sizeof(uint32_t) * cap);
+    c->nframes = 0;
+    while (pos + 12 <= c->size) {
+        const uint8_t *p = c->data + pos;
+        uint32_t n = p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24);
+        pos += 12;
+        if (pos + n > c->size) break;
+        if (c->nframes == cap) {
+            cap *= 2;
+            c->off = (size_t *)realloc(c->off, sizeof(size_t) * cap);
+            c->len = (uint32_t *)realloc(c->len, sizeof(uint32_t) * cap);
+        }
+        c->off[c->nframes] = pos; c->len[c->nframes] = n; c->nframes++;
+        pos += n;
+    }
+}
+
+static long decode_one(inst_t *in, int f, uint64_t *sum)
+{
+    const clip_t *c = in->clip;
+    vpx_codec_iter_t it = NULL;
+    vpx_image_t *img;
+    long shown = 0;
+    if (vpx_codec_decode(&in->dec, c->data + c->off[f], c->len[f], NULL, 0)) {
+        fprintf(stderr, "decode failed: %s (%s)\n", vpx_codec_error(&in->dec),
+                vpx_codec_error_detail(&in->dec) ? vpx_codec_error_detail(&in->dec) : "");
+        exit(3);
+    }
+    while ((img = vpx_codec_get_frame(&in->dec, &it))) {
+        shown++;
+        if (sum) {
+            unsigned y, x;
+            uint64_t s = 0;
+            for (y = 0; y < img->d_h; y++) {
+                const uint8_t *r = img->planes[0] + (size_t)y * img->stride[0];
+                for (x = 0; x < img->d_w; x++) s += r[x];
+            }
+            for (y = 0; y < (img->d_h + 1) / 2; y++) {
+                const uint8_t *r1 = img->planes[1] + (size_t)y * img->stride[1];
+                const uint8_t *r2 = img->planes[2] + (size_t)y * img->stride[2];
+                for (x = 0; x < (img->d_w + 1) / 2; x++) s += r1[x] + r2[x];
+            }
+            *sum += s;
+        } else {
+            /* touch one byte per plane so the frame is really consumed from host memory */
+            volatile uint8_t t = img->planes[0][0] ^ img->planes[1][0] ^ img->planes[2][0];
+            (void)t;
+        }
+    }
+    return shown;
+}
+
+static void *worker(void *arg)
+{
+    int t = (int)(intptr_t)arg, i, f, r, maxf = 0;
+    long n = 0;
+    for (i = t; i < g_streams; i += g_threads) {
+        vpx_codec_dec_cfg_t cfg = {0};
+        inst_t *in = &g_inst[i];
+        in->clip = &g_clips[i % g_nclips];
+        if (vpx_codec_dec_init(&in->dec, vpx_codec_vp8_dx(), &cfg, 0)) { fprintf(stderr, "init failed\n"); exit(3); }
+        if (in->clip->nframes > maxf) maxf = in->clip->nframes;
+    }
+    /* warm-up pass (untimed): creates the device contexts, pins memory */
+    for (f = 0; f < maxf; f++)
+        for (i = t; i < g_streams; i += g_threads)
+            if (f < g_inst[i].clip->nframes) decode_one(&g_inst[i], f, NULL);
+    pthread_barrier_wait(&g_bar);
+    if (t == 0) g_t0 = now_s();
+    pthread_barrier_wait(&g_bar);
+    for (r = 0; r < g_repeat; r++)
+        for (f = 0; f < maxf; f++)
+            for (i = t; i < g_streams; i += g_threads)
+                if (f < g_inst[i].clip->nframes)
+                    n += decode_one(&g_inst[i], f, (g_sum && i == 0 && r == g_repeat - 1) ? &g_checksum : NULL);
+    g_t1[t] = now_s();
+    g_frames[t] = n;
+    pthread_barrier_wait(&g_bar);
+    for (i = t; i < g_streams; i += g_threads) vpx_codec_destroy(&g_inst[i].dec);
+    return NULL;
+}
+
+int main(int argc, char **argv)
+{
+    pthread_t th[1024];
+    int i;
+    long total = 0;
+    double tend = 0;
+    uint64_t st0[4], st1[4];
+    for (i = 1; i < argc; i++) {
+        if (!strcmp(argv[i], "--threads") && i + 1 < argc) g_threads = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--streams") && i + 1 < argc) g_streams = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--repeat") && i + 1 < argc) g_repeat = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--sum")) g_sum = 1;
+        else if (g_nclips < 1024) load_clip(&g_clips[g_nclips++], argv[i]);
+    }
+    if (!g_nclips) { fprintf(stderr, "usage: b200bench [--threads T] [--streams S] [--repeat R] [--sum] a.ivf ...\n"); return 2; }
+    if (g_threads > g_streams) g_threads = g_streams;
+    if (g_threads > 1024) g_threads = 1024;
+    g_inst = (inst_t *)calloc((size_t)g_streams, sizeof(inst_t));
+    pthread_barrier_init(&g_bar, NULL, (unsigned)g_threads);
+    for (i = 0; i < g_threads; i++) pthread_create(&th[i], NULL, worker, (void *)(intptr_t)i);
+    /* stats snapshot is taken by differencing around the whole run minus warm-up: the
+     * workers are symmetric, so scale by the timed share */
+    vp8b200_global_stats(st0);
+    for (i = 0; i < g_threads; i++) pthread_join(th[i], NULL);
+    vp8b200_global_stats(st1);
+    for (i = 0; i < g_threads; i++) { total += g_frames[i]; if (g_t1[i] > tend) tend = g_t1[i]; }
+    {
+        /* warm-up = 1 pass, timed = g_repeat passes: per-frame byte counts are identical */
+        double share = (double)g_repeat / (double)(g_repeat + 1);
+        printf("{\"frames\": %ld, \"wall_s\": %.6f, \"fps\": %.3f, \"threads\": %d, \"streams\": %d, "
+               "\"repeat\": %d, \"h2d_bytes\": %.0f, \"d2h_bytes\": %.0f, \"kernel_launches\": %.0f, "
+               "\"checksum\": %llu}\n",
+               total, tend - g_t0, total / (tend - g_t0), g_threads, g_streams, g_repeat,
+               (double)(st1[0] - st0[0]) * share, (double)(st1[1] - st0[1]) * share,
+               (double)(st1[2] - st0[2]) * share, (unsigned long long)g_checksum);
+    }
+    return 0;
+}

@@ -39,6 +39,8 @@
  * success or a negative vp8b200_status; none throws, none uses process globals, contexts
  * are independent (thread-compatible: one thread per context at a time).  There is NO CPU
  * fallback: if no CUDA device is usable vp8b200_create fails with VP8B200_ERR_NO_DEVICE.
+ * Environment: VP8B200_SYNC=block makes frame_fetch sleep on an event instead of spinning
+ * (many decoder threads per core).
  */
 #ifndef VP8B200_H
 #define VP8B200_H
@@ -186,6 +188,15 @@ void vp8b200_staged_free(vp8b200_ctx *ctx, vp8b200_staged *s);
 /* Reconstruct frame[i] on ctx[i] for i < n with ONE launch of each kernel covering all n
  * streams (all contexts must share device and geometry).  Asynchronous on ctx[0]'s stream. */
 int  vp8b200_batch_run(vp8b200_ctx *const *ctx, vp8b200_staged *const *frame, int n);
+
+/* process-wide monotonic counters: [0] bytes copied host->device, [1] device->host,
+ * [2] kernels launched, [3] frames reconstructed */
+void vp8b200_global_stats(uint64_t out[4]);
+/* per-kernel device timing (CUDA events around every launch on the context's stream):
+ * kind 0 inter prediction+residual, 1 intra wavefront, 2 loop filter, 3 border extension.
+ * profile_read waits for the stream, returns accumulated ms / launch counts and resets. */
+int  vp8b200_profile_enable(vp8b200_ctx *ctx, int enable);
+int  vp8b200_profile_read(vp8b200_ctx *ctx, double ms[4], uint64_t count[4]);
 
 /* number of kernels this library has launched on the context (for bench accounting) */
 uint64_t vp8b200_launch_count(const vp8b200_ctx *ctx);

@@ -11,8 +11,15 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
 #include <new>
+#include <vector>
 #include "vp8b200_internal.h"
+
+/* process-wide statistics (monotonic counters only; no behaviour depends on them) */
+static std::atomic<uint64_t> g_h2d_bytes{0}, g_d2h_bytes{0}, g_launches{0}, g_frames{0};
+
+struct ProfSpan { int kind; cudaEvent_t a, b; };
 
 #define NSLOT 3          /* pinned/device record slots: parse N+1 while N uploads / runs */
 #define NBJOB 4          /* job-array ring for batched launches */
@@ -56,6 +63,10 @@ struct vp8b200_ctx {
     bool bjobs_pending[NBJOB];
     int bjobs_cap, bjobs_cur;
     uint64_t launches;
+    bool blocking_sync;            /* VP8B200_SYNC=block: sleep instead of spinning in fetch */
+    cudaEvent_t fetch_done;
+    bool profiling;
+    std::vector<ProfSpan> *spans;
     char err[256];
 };
 
@@ -119,6 +130,11 @@ static void free_ctx(vp8b200_ctx *c)
         if (c->bjobs_done[i]) cudaEventDestroy(c->bjobs_done[i]);
     }
     cudaFree(c->d_progress); cudaFree(c->d_tickets);
+    if (c->fetch_done) cudaEventDestroy(c->fetch_done);
+    if (c->spans) {
+        for (auto &sp : *c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+        delete c->spans;
+    }
     if (c->stream) cudaStreamDestroy(c->stream);
     cudaGetLastError();
     delete c;
@@ -153,6 +169,12 @@ static int create_impl(vp8b200_ctx *c)
     CK(c, cudaMemsetAsync(c->d_progress, 0, 2 * g.mb_rows * sizeof(unsigned), c->stream));
     CK(c, cudaMalloc((void **)&c->d_tickets, 2 * sizeof(unsigned)));
     CK(c, cudaMemsetAsync(c->d_tickets, 0, 2 * sizeof(unsigned), c->stream));
+    {
+        const char *e = getenv("VP8B200_SYNC");
+        c->blocking_sync = e && !strcmp(e, "block");
+        CK(c, cudaEventCreateWithFlags(&c->fetch_done, cudaEventDisableTiming |
+                                       (c->blocking_sync ? cudaEventBlockingSync : 0)));
+    }
     CK(c, cudaStreamSynchronize(c->stream));
     return VP8B200_OK;
 }
@@ -287,20 +309,46 @@ static void fill_job(vp8b200_ctx *c, FrameJob *j, const vp8b200_frame_hdr &h, co
 }
 
 /* the launch sequence shared by frame_submit (n = 1) and batch_run */
+static void prof_mark(vp8b200_ctx *c, int kind, bool begin)
+{
+    if (!c->profiling) return;
+    if (begin) {
+        ProfSpan sp; sp.kind = kind;
+        cudaEventCreate(&sp.a); cudaEventCreate(&sp.b);
+        cudaEventRecord(sp.a, c->stream);
+        c->spans->push_back(sp);
+    } else {
+        cudaEventRecord(c->spans->back().b, c->stream);
+    }
+}
+
 static int run_jobs(vp8b200_ctx *c, const FrameJob *d_jobs, int n, bool any_inter, bool any_intra, bool any_lf)
 {
     int nctas = 0;
-    if (any_inter) { vp8b200_launch_inter(c->stream, d_jobs, n, c->geo); c->launches++; }
+    unsigned k = 0;
+    if (any_inter) {
+        prof_mark(c, 0, true);
+        vp8b200_launch_inter(c->stream, d_jobs, n, c->geo);
+        prof_mark(c, 0, false); k++;
+    }
     if (any_intra) {
+        prof_mark(c, 1, true);
         vp8b200_launch_intra(c->stream, d_jobs, n, c->geo, c->d_tickets + 0, c->ticket_base[0], &nctas);
-        c->ticket_base[0] += (unsigned)nctas; c->launches++;
+        prof_mark(c, 1, false);
+        c->ticket_base[0] += (unsigned)nctas; k++;
     }
     if (any_lf) {
+        prof_mark(c, 2, true);
         vp8b200_launch_loopfilter(c->stream, d_jobs, n, c->geo, c->d_tickets + 1, c->ticket_base[1], &nctas);
-        c->ticket_base[1] += (unsigned)nctas; c->launches++;
+        prof_mark(c, 2, false);
+        c->ticket_base[1] += (unsigned)nctas; k++;
     }
+    prof_mark(c, 3, true);
     vp8b200_launch_border(c->stream, d_jobs, n, c->geo);
-    c->launches++;
+    prof_mark(c, 3, false); k++;
+    c->launches += k;
+    g_launches += k;
+    g_frames += (uint64_t)n;
     CK(c, cudaGetLastError());
     return VP8B200_OK;
 }
@@ -327,6 +375,8 @@ extern "C" int vp8b200_frame_submit(vp8b200_ctx *c, uint32_t n_aux, uint32_t n_c
     CK(c, cudaMemcpyAsync(s.d_job, s.h_job, sizeof(FrameJob), cudaMemcpyHostToDevice, c->stream));
     CK(c, cudaEventRecord(s.h2d_done, c->stream));
     s.pending = true;
+    g_h2d_bytes += (uint64_t)c->n_mb * sizeof(vp8b200_mb) + (uint64_t)n_aux * sizeof(vp8b200_aux) +
+                   (uint64_t)n_coef * 32 + sizeof(FrameJob);
     int st = run_jobs(c, s.d_job, 1, !key, run_intra, run_lf);
     c->cur = (c->cur + 1) % NSLOT;
     return st;
@@ -337,7 +387,13 @@ extern "C" int vp8b200_frame_fetch(vp8b200_ctx *c, int fb, uint8_t *dst, size_t 
     if (!c || fb < 0 || fb >= c->n_fb || !dst || bytes > c->frame_size) return VP8B200_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaMemcpyAsync(dst, c->fb[fb], bytes, cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaStreamSynchronize(c->stream));
+    if (c->blocking_sync) {
+        CK(c, cudaEventRecord(c->fetch_done, c->stream));
+        CK(c, cudaEventSynchronize(c->fetch_done));
+    } else {
+        CK(c, cudaStreamSynchronize(c->stream));
+    }
+    g_d2h_bytes += bytes;
     return VP8B200_OK;
 }
 
@@ -451,8 +507,43 @@ extern "C" int vp8b200_batch_run(vp8b200_ctx *const *ctx, vp8b200_staged *const 
                  any_intra, any_lf && s->hdr.filter_level != 0);
     }
     CK(c, cudaMemcpyAsync(c->d_bjobs[r], c->h_bjobs[r], (size_t)n * sizeof(FrameJob), cudaMemcpyHostToDevice, c->stream));
+    g_h2d_bytes += (uint64_t)n * sizeof(FrameJob);
     CK(c, cudaEventRecord(c->bjobs_done[r], c->stream));
     c->bjobs_pending[r] = true;
     c->bjobs_cur = (r + 1) % NBJOB;
     return run_jobs(c, c->d_bjobs[r], n, any_inter, any_intra, any_lf);
+}
+
+/* ---- statistics and per-kernel profiling -------------------------------------------------- */
+
+extern "C" void vp8b200_global_stats(uint64_t out[4])
+{
+    out[0] = g_h2d_bytes.load(); out[1] = g_d2h_bytes.load();
+    out[2] = g_launches.load(); out[3] = g_frames.load();
+}
+
+extern "C" int vp8b200_profile_enable(vp8b200_ctx *c, int enable)
+{
+    if (!c) return VP8B200_ERR_INVALID;
+    if (!c->spans) c->spans = new (std::nothrow) std::vector<ProfSpan>();
+    if (!c->spans) return VP8B200_ERR_NOMEM;
+    c->profiling = enable != 0;
+    return VP8B200_OK;
+}
+
+extern "C" int vp8b200_profile_read(vp8b200_ctx *c, double ms[4], uint64_t count[4])
+{
+    if (!c || !ms || !count) return VP8B200_ERR_INVALID;
+    for (int i = 0; i < 4; i++) { ms[i] = 0; count[i] = 0; }
+    if (!c->spans) return VP8B200_OK;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    for (auto &sp : *c->spans) {
+        float t = 0;
+        CK(c, cudaEventElapsedTime(&t, sp.a, sp.b));
+        ms[sp.kind] += t; count[sp.kind]++;
+        cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
+    }
+    c->spans->clear();
+    return VP8B200_OK;
 }

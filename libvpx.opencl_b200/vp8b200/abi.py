@@ -17,7 +17,8 @@ EXPORTS = [
     "vp8b200_host_alloc", "vp8b200_host_free", "vp8b200_frame_begin", "vp8b200_frame_submit",
     "vp8b200_frame_abort", "vp8b200_frame_fetch", "vp8b200_frame_upload", "vp8b200_frame_copy",
     "vp8b200_sync", "vp8b200_stage_frame", "vp8b200_staged_free", "vp8b200_batch_run",
-    "vp8b200_launch_count", "vp8b200_stream",
+    "vp8b200_launch_count", "vp8b200_stream", "vp8b200_global_stats", "vp8b200_profile_enable",
+    "vp8b200_profile_read",
 ]
 
 
@@ -61,6 +62,10 @@ def lib():
         L.vp8b200_launch_count.argtypes = [C.c_void_p]
         L.vp8b200_stream.restype = C.c_void_p
         L.vp8b200_stream.argtypes = [C.c_void_p]
+        L.vp8b200_global_stats.restype = None
+        L.vp8b200_global_stats.argtypes = [C.POINTER(C.c_uint64)]
+        L.vp8b200_profile_enable.argtypes = [C.c_void_p, C.c_int]
+        L.vp8b200_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 
@@ -142,11 +147,27 @@ class Context:
         self._staged.append(s)
         return s
 
+    def profile(self, enable=True):
+        self._ck(self.L.vp8b200_profile_enable(self.h, int(enable)), "profile_enable")
+
+    def profile_read(self):
+        """{kernel: (total ms, launches)} since the last read; waits for the stream."""
+        ms = (C.c_double * 4)()
+        n = (C.c_uint64 * 4)()
+        self._ck(self.L.vp8b200_profile_read(self.h, ms, n), "profile_read")
+        return {k: (ms[i], int(n[i])) for i, k in enumerate(("inter", "intra", "loopfilter", "border"))}
+
     def launch_count(self):
         return int(self.L.vp8b200_launch_count(self.h))
 
     def stream(self):
         return self.L.vp8b200_stream(self.h)
+
+
+def global_stats():
+    out = (C.c_uint64 * 4)()
+    lib().vp8b200_global_stats(out)
+    return {"h2d_bytes": int(out[0]), "d2h_bytes": int(out[1]), "launches": int(out[2]), "frames": int(out[3])}
 
 
 def batch_run(ctxs, staged):
