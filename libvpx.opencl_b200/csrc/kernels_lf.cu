@@ -179,8 +179,6 @@ k_loopfilter(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g,
     uint8_t *rowp = plane + (size_t)(mb_row * mbw + pi) * stride;      /* my pixel row, x = 0 */
     const bool lane_on = luma || !simple;                  /* simple filter: luma only */
     uint8_t *tile = s_tile[warp] + (luma ? 0 : (lane < 24 ? 320 : 416));
-    const int tw = mbw;                                    /* tile row pitch: 16 / 8 bytes */
-    const int nw = luma ? 4 : 2;                           /* words per pixel row */
     const bool top = mb_row > 0;
 
     const unsigned *mbrec = reinterpret_cast<const unsigned *>(job.mb + (size_t)mb_row * g.mb_cols);
@@ -190,6 +188,7 @@ k_loopfilter(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g,
         else { uint2 v = *reinterpret_cast<const uint2 *>(rowp); cur[0] = v.x; cur[1] = v.y; }
     }
     unsigned rec = mbrec[0], rec_n = 0;
+    unsigned seen = base;                                  /* last value read from up_prog */
 
     for (int c = 0; c < g.mb_cols; c++) {
         /* prefetch the next macroblock's rows and record */
@@ -244,9 +243,19 @@ k_loopfilter(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g,
             if (top) {
                 /* row above must have finished iteration c+1 (which stores the last 4
                  * columns of its MB c); for the last column that is its end-of-row flush,
-                 * published as mb_cols+1 */
-                unsigned need = base + (unsigned)(c + 2);
-                while ((int)(lf_ld_acquire(up_prog) - need) < 0) __nanosleep(20);
+                 * published as mb_cols+1.  The counter is re-read only when the value seen
+                 * last time is not enough (the row above is usually several MBs ahead);
+                 * lane 0 polls, the acquire is extended to the warp by __syncwarp. */
+                const unsigned need = base + (unsigned)(c + 2);
+                if ((int)(seen - need) < 0) {
+                    if (lane == 0) {
+                        unsigned v = lf_ld_acquire(up_prog);
+                        while ((int)(v - need) < 0) { __nanosleep(40); v = lf_ld_acquire(up_prog); }
+                        seen = v;
+                    }
+                    seen = __shfl_sync(FULL_MASK, seen, 0);
+                    __syncwarp();                  /* order every lane's loads after the acquire */
+                }
                 if (lane_on && pi < 4) {
                     const uint8_t *ap = plane + (size_t)(mb_row * mbw - 4 + pi) * stride + c * mbw;
                     if (luma) *reinterpret_cast<uint4 *>(tile + pi * 16) = __ldcg(reinterpret_cast<const uint4 *>(ap));
@@ -293,8 +302,9 @@ k_loopfilter(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g,
             }
             __syncwarp();
         }
-        /* publish: columns < c are final for the row below once c+1 is published */
-        __threadfence();
+        /* publish: columns < c are final for the row below once c+1 is published.  One
+         * release by lane 0 after the warp barrier covers every lane's stores (the barrier
+         * orders them before the release; release is cumulative). */
         __syncwarp();
         if (lane == 0) lf_st_release(my_prog, base + c + 1);
         rec = rec_n;
@@ -303,7 +313,6 @@ k_loopfilter(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g,
     }
     /* last 4 columns of the row */
     if (lane_on) *reinterpret_cast<unsigned *>(rowp + g.mb_cols * mbw - 4) = halo;
-    __threadfence();
     __syncwarp();
     if (lane == 0) lf_st_release(my_prog, base + g.mb_cols + 1);
 }

@@ -237,11 +237,6 @@ __device__ __forceinline__ void st_release(unsigned *p, unsigned v)
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-/* spin until *p has reached `target` in this frame's epoch (wrap-safe compare) */
-__device__ __forceinline__ void wait_progress(const unsigned *p, unsigned target)
-{
-    while ((int)(ld_acquire(p) - target) < 0) __nanosleep(20);
-}
 
 /* reconintra4x4.c:16-296.  A[0] = top-left, A[1..8] = above + above-right, L[0..3] = left. */
 __device__ __forceinline__ void intra4x4(int mode, const int (&A)[9], const int (&L)[4], unsigned (&px)[4])
@@ -436,6 +431,7 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g,
     uint8_t *UT = s_ct[warp][0], *VT = s_ct[warp][1];
     uint8_t *const dy = job.dst + g.y_off, *const du = job.dst + g.u_off, *const dv = job.dst + g.v_off;
     const bool up = mb_row != 0;
+    unsigned seen = base;                                /* last value read from up_prog */
 
     for (int c0 = 0; c0 < g.mb_cols; c0 += 32) {
         /* scan 32 macroblock records at a time for intra ones */
@@ -455,8 +451,16 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g,
             if (lane == 0) st_release(my_prog, base + mb_col);
             /* dependency: row above finished column mb_col+1 (above-right), clamped to the row end */
             if (up) {
-                unsigned need = (unsigned)min(mb_col + 2, g.mb_cols);
-                wait_progress(up_prog, base + need);
+                const unsigned need = base + (unsigned)min(mb_col + 2, g.mb_cols);
+                if ((int)(seen - need) < 0) {
+                    if (lane == 0) {
+                        unsigned v = ld_acquire(up_prog);
+                        while ((int)(v - need) < 0) { __nanosleep(40); v = ld_acquire(up_prog); }
+                        seen = v;
+                    }
+                    seen = __shfl_sync(FULL_MASK, seen, 0);
+                    __syncwarp();                  /* order every lane's loads after the acquire */
+                }
             }
             __syncwarp();
             /* ---- borders into the tiles (setupintrarecon.c:15-32 rules at frame edges) ---- */
@@ -540,8 +544,8 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g,
                     __syncwarp();
                 }
             }
-            /* publish: everything up to and including this column of the row is final */
-            __threadfence();
+            /* publish: everything up to and including this column of the row is final
+             * (warp barrier, then one cumulative release by lane 0) */
             __syncwarp();
             if (lane == 0) st_release(my_prog, base + mb_col + 1);
         }

@@ -7,9 +7,9 @@
  *
  * Parity status: PINNED.  (a) tests/test_oracle_vs_reference.py checks every function here
  * against the unmodified reference compiled from /root/reference (oracle/_ref/libvpxref.so)
- * on seeded random inputs; (b) tests/test_golden_streams.py replays committed record dumps
+ * on seeded random inputs; (b) tests/test_oracle_golden.py replays committed record dumps
  * of reference-encoded streams and requires the per-frame MD5s printed by the reference's
- * own `vpxdec --md5` (tests/golden/*.md5).  The reference tree itself holds no golden
+ * own `vpxdec --md5` (tests/golden/<case>.md5).  The reference tree itself holds no golden
  * vectors, so the pins are generated from the reference, with the
  * generating scripts committed (tools/make_golden.py).
  *
@@ -632,7 +632,7 @@ static void lf_simple(uint8_t *s, int st, int blim)
 }
 
 /* one edge of `n` pixels; `along` = step between the n pixels, `across` = step across it */
-static void edge_normal(uint8_t *s, int along, int across, int n, int mbedge,
+void oracle_edge_normal(uint8_t *s, int along, int across, int n, int mbedge,
                         int elim, int ilim, int thr)
 {
     int i;
@@ -642,7 +642,7 @@ static void edge_normal(uint8_t *s, int along, int across, int n, int mbedge,
             if (mbedge) lf_mbedge(s, across, hev); else lf_inner(s, across, hev);
         }
 }
-static void edge_simple(uint8_t *s, int along, int across, int n, int blim)
+void oracle_edge_simple(uint8_t *s, int along, int across, int n, int blim)
 {
     int i;
     for (i = 0; i < n; i++, s += along) lf_simple(s, across, blim);
@@ -722,30 +722,30 @@ static void loop_filter_frame(const oracle_dec *d, const vp8b200_frame_hdr *hdr,
             else thr = level >= 40 ? 3 : (level >= 20 ? 2 : (level >= 15 ? 1 : 0));
             if (hdr->filter_type == 0) {
                 if (c > 0) {
-                    edge_normal(y, ys, 1, 16, 1, mblim, ilim, thr);
-                    edge_normal(u, us, 1, 8, 1, mblim, ilim, thr);
-                    edge_normal(v, us, 1, 8, 1, mblim, ilim, thr);
+                    oracle_edge_normal(y, ys, 1, 16, 1, mblim, ilim, thr);
+                    oracle_edge_normal(u, us, 1, 8, 1, mblim, ilim, thr);
+                    oracle_edge_normal(v, us, 1, 8, 1, mblim, ilim, thr);
                 }
                 if (!skip_lf) {
-                    for (k = 4; k < 16; k += 4) edge_normal(y + k, ys, 1, 16, 0, blim, ilim, thr);
-                    edge_normal(u + 4, us, 1, 8, 0, blim, ilim, thr);
-                    edge_normal(v + 4, us, 1, 8, 0, blim, ilim, thr);
+                    for (k = 4; k < 16; k += 4) oracle_edge_normal(y + k, ys, 1, 16, 0, blim, ilim, thr);
+                    oracle_edge_normal(u + 4, us, 1, 8, 0, blim, ilim, thr);
+                    oracle_edge_normal(v + 4, us, 1, 8, 0, blim, ilim, thr);
                 }
                 if (r > 0) {
-                    edge_normal(y, 1, ys, 16, 1, mblim, ilim, thr);
-                    edge_normal(u, 1, us, 8, 1, mblim, ilim, thr);
-                    edge_normal(v, 1, us, 8, 1, mblim, ilim, thr);
+                    oracle_edge_normal(y, 1, ys, 16, 1, mblim, ilim, thr);
+                    oracle_edge_normal(u, 1, us, 8, 1, mblim, ilim, thr);
+                    oracle_edge_normal(v, 1, us, 8, 1, mblim, ilim, thr);
                 }
                 if (!skip_lf) {
-                    for (k = 4; k < 16; k += 4) edge_normal(y + k * ys, 1, ys, 16, 0, blim, ilim, thr);
-                    edge_normal(u + 4 * us, 1, us, 8, 0, blim, ilim, thr);
-                    edge_normal(v + 4 * us, 1, us, 8, 0, blim, ilim, thr);
+                    for (k = 4; k < 16; k += 4) oracle_edge_normal(y + k * ys, 1, ys, 16, 0, blim, ilim, thr);
+                    oracle_edge_normal(u + 4 * us, 1, us, 8, 0, blim, ilim, thr);
+                    oracle_edge_normal(v + 4 * us, 1, us, 8, 0, blim, ilim, thr);
                 }
             } else {
-                if (c > 0) edge_simple(y, ys, 1, 16, mblim);
-                if (!skip_lf) for (k = 4; k < 16; k += 4) edge_simple(y + k, ys, 1, 16, blim);
-                if (r > 0) edge_simple(y, 1, ys, 16, mblim);
-                if (!skip_lf) for (k = 4; k < 16; k += 4) edge_simple(y + k * ys, 1, ys, 16, blim);
+                if (c > 0) oracle_edge_simple(y, ys, 1, 16, mblim);
+                if (!skip_lf) for (k = 4; k < 16; k += 4) oracle_edge_simple(y + k, ys, 1, 16, blim);
+                if (r > 0) oracle_edge_simple(y, 1, ys, 16, mblim);
+                if (!skip_lf) for (k = 4; k < 16; k += 4) oracle_edge_simple(y + k * ys, 1, ys, 16, blim);
             }
         }
 }
