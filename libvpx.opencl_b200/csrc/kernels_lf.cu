@@ -6,123 +6,141 @@
  *
  * Schedule: the reference filters macroblocks in raster order and each macroblock reads
  * pixels its left, above and above-right neighbours have already modified.  One warp owns
- * one macroblock ROW and walks it left to right; row r may filter column c once row r-1 has
- * finished column c+1 (per-row progress counters in global memory, release/acquire).
+ * one macroblock ROW and walks it left to right; row r can do the horizontal edges of column
+ * c once row r-1 has done the left edge of column c+1.  There are no flags and no fences on
+ * that path: a row hands the bottom 4 pixel rows of each finished macroblock DOWN as a
+ * message and the row below finishes (top-edge filter) and stores the 3 rows it modifies.
+ *   - rows in the same CTA: message through a shared-memory ring (LF_RING slots per row);
+ *   - across CTAs: tagged 64-bit words in global memory, {32 bits of pixels, 32-bit frame
+ *     tag}; an aligned 64-bit access is single-copy atomic, so a word whose tag matches
+ *     carries valid pixels and the consumer simply polls the words (NCCL's LL idea).
  *
- * Inside a macroblock the warp first filters the four vertical edges with lane = pixel row
- * (lanes 0-15 luma rows, 16-23 U rows, 24-31 V rows; the row lives in registers, the 4
- * pixels left of the MB are carried over from the previous column), transposes through a
- * 512-byte shared-memory tile, filters the four horizontal edges with lane = pixel column,
- * and transposes back.  The last 4 columns of a macroblock are stored one iteration later,
- * after the next macroblock's left-edge filter has modified them.
+ * Inside a macroblock the warp first filters the vertical edges with lane = pixel row
+ * (lanes 0-15 luma rows, 16-23 U rows, 24-31 V rows; rows live in registers, the 4 pixels
+ * left of the MB are carried over from the previous column), transposes through a 512-byte
+ * shared-memory tile, filters the horizontal edges with lane = pixel column, and transposes
+ * back.  The last 4 columns of a macroblock are stored one iteration later, after the next
+ * macroblock's left-edge filter has modified them.  Filters are branch-free (select on the
+ * mask) so that a lane's instruction stream is short and free of divergence; macroblocks
+ * without inner edges (skip_lf) only move the 8 rows the top edge needs through the tile.
  */
 #include "vp8b200_dev.cuh"
 
 #define LF_ROWS_PER_CTA 4
-
-__device__ __forceinline__ unsigned lf_ld_acquire(const unsigned *p)
-{
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void lf_st_release(unsigned *p, unsigned v)
-{
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
+#define LF_RING 4                 /* shared-memory message slots per row (power of two) */
 
 __device__ __forceinline__ int sc(int v) { return max(min(v, 127), -128); }
+__device__ __forceinline__ int ad(int a, int b) { return __sad(a, b, 0); }      /* |a-b|, one VABSDIFF */
+__device__ __forceinline__ int c255(int v) { return __vimin_s32_relu(v, 255); }  /* clamp to 0..255 */
 
 struct LfParams { int ilim, blim, mblim, thr; };
 
-/* loopfilter_filters.c:27-49 on ints */
+/* loopfilter_filters.c:27-49; pixels as plain 0..255 ints */
 __device__ __forceinline__ bool lf_mask(int p3, int p2, int p1, int p0, int q0, int q1, int q2, int q3,
                                         int ilim, int elim)
 {
-    int m = max(max(abs(p3 - p2), abs(p2 - p1)), max(abs(p1 - p0), abs(q1 - q0)));
-    m = max(m, max(abs(q2 - q1), abs(q3 - q2)));
-    return m <= ilim && abs(p0 - q0) * 2 + (abs(p1 - q1) >> 1) <= elim;
+    int m = max(__vimax3_s32(ad(p3, p2), ad(p2, p1), ad(p1, p0)), __vimax3_s32(ad(q1, q0), ad(q2, q1), ad(q3, q2)));
+    return m <= ilim && ad(p0, q0) * 2 + (ad(p1, q1) >> 1) <= elim;
 }
 
-/* inner edge: loopfilter_filters.c:51-97 */
+/* inner edge: loopfilter_filters.c:51-97.  sc(qs0 - F) + 128 == clamp(q0 - F, 0, 255), so the
+ * signed-char arithmetic of the reference is done directly on pixel values. */
 __device__ __forceinline__ void lf_inner(int p3, int p2, int &p1, int &p0, int &q0, int &q1, int q2, int q3,
                                          const LfParams &P)
 {
-    if (!lf_mask(p3, p2, p1, p0, q0, q1, q2, q3, P.ilim, P.blim)) return;
-    bool hev = abs(p1 - p0) > P.thr || abs(q1 - q0) > P.thr;
-    int ps1 = p1 - 128, ps0 = p0 - 128, qs0 = q0 - 128, qs1 = q1 - 128;
-    int f = hev ? sc(ps1 - qs1) : 0;
-    f = sc(f + 3 * (qs0 - ps0));
-    int f1 = sc(f + 4) >> 3, f2 = sc(f + 3) >> 3;
-    q0 = sc(qs0 - f1) + 128;
-    p0 = sc(ps0 + f2) + 128;
-    int u = hev ? 0 : (f1 + 1) >> 1;
-    q1 = sc(qs1 - u) + 128;
-    p1 = sc(ps1 + u) + 128;
+    const bool mask = lf_mask(p3, p2, p1, p0, q0, q1, q2, q3, P.ilim, P.blim);
+    const bool hev = max(ad(p1, p0), ad(q1, q0)) > P.thr;
+    int f = hev ? sc(p1 - q1) : 0;
+    f = sc(f + 3 * (q0 - p0));
+    f = mask ? f : 0;
+    const int f1 = min(f + 4, 127) >> 3, f2 = min(f + 3, 127) >> 3;
+    const int u = hev ? 0 : (f1 + 1) >> 1;
+    q0 = c255(q0 - f1);
+    p0 = c255(p0 + f2);
+    q1 = c255(q1 - u);
+    p1 = c255(p1 + u);
 }
 
 /* macroblock edge: loopfilter_filters.c:161-214 */
 __device__ __forceinline__ void lf_mbedge(int p3, int &p2, int &p1, int &p0, int &q0, int &q1, int &q2, int q3,
                                           const LfParams &P)
 {
-    if (!lf_mask(p3, p2, p1, p0, q0, q1, q2, q3, P.ilim, P.mblim)) return;
-    bool hev = abs(p1 - p0) > P.thr || abs(q1 - q0) > P.thr;
-    int ps2 = p2 - 128, ps1 = p1 - 128, ps0 = p0 - 128, qs0 = q0 - 128, qs1 = q1 - 128, qs2 = q2 - 128;
-    int f = sc(sc(ps1 - qs1) + 3 * (qs0 - ps0));
-    int g = hev ? f : 0;
-    int f1 = sc(g + 4) >> 3, f2 = sc(g + 3) >> 3;
-    qs0 = sc(qs0 - f1);
-    ps0 = sc(ps0 + f2);
-    if (hev) f = 0;
-    int u = sc((63 + f * 27) >> 7);
-    q0 = sc(qs0 - u) + 128;
-    p0 = sc(ps0 + u) + 128;
-    u = sc((63 + f * 18) >> 7);
-    q1 = sc(qs1 - u) + 128;
-    p1 = sc(ps1 + u) + 128;
-    u = sc((63 + f * 9) >> 7);
-    q2 = sc(qs2 - u) + 128;
-    p2 = sc(ps2 + u) + 128;
+    const bool mask = lf_mask(p3, p2, p1, p0, q0, q1, q2, q3, P.ilim, P.mblim);
+    const bool hev = max(ad(p1, p0), ad(q1, q0)) > P.thr;
+    int f = sc(sc(p1 - q1) + 3 * (q0 - p0));
+    f = mask ? f : 0;
+    const int g = hev ? f : 0, w = hev ? 0 : f;
+    const int f1 = min(g + 4, 127) >> 3, f2 = min(g + 3, 127) >> 3;
+    /* |(63 + w*k) >> 7| <= 27: the reference's clamp of u is a no-op */
+    const int u27 = (63 + w * 27) >> 7, u18 = (63 + w * 18) >> 7, u9 = (63 + w * 9) >> 7;
+    q0 = c255(c255(q0 - f1) - u27);
+    p0 = c255(c255(p0 + f2) + u27);
+    q1 = c255(q1 - u18);
+    p1 = c255(p1 + u18);
+    q2 = c255(q2 - u9);
+    p2 = c255(p2 + u9);
 }
 
 /* simple filter: loopfilter_filters.c:281-315 */
 __device__ __forceinline__ void lf_simple(int p1, int &p0, int &q0, int q1, int blim)
 {
-    if (abs(p0 - q0) * 2 + (abs(p1 - q1) >> 1) > blim) return;
-    int f = sc(sc((p1 - 128) - (q1 - 128)) + 3 * (q0 - p0));
-    int f1 = sc(f + 4) >> 3, f2 = sc(f + 3) >> 3;
-    q0 = sc(q0 - 128 - f1) + 128;
-    p0 = sc(p0 - 128 + f2) + 128;
+    const bool mask = ad(p0, q0) * 2 + (ad(p1, q1) >> 1) <= blim;
+    int f = sc(sc(p1 - q1) + 3 * (q0 - p0));
+    f = mask ? f : 0;
+    q0 = c255(q0 - (min(f + 4, 127) >> 3));
+    p0 = c255(p0 + (min(f + 3, 127) >> 3));
 }
 
 __device__ __forceinline__ void unpack(unsigned w, int &a, int &b, int &c, int &d)
 {
-    a = w & 255; b = (w >> 8) & 255; c = (w >> 16) & 255; d = w >> 24;
+    a = __byte_perm(w, 0, 0x4440); b = __byte_perm(w, 0, 0x4441);
+    c = __byte_perm(w, 0, 0x4442); d = __byte_perm(w, 0, 0x4443);
+}
+__device__ __forceinline__ unsigned pack(int a, int b, int c, int d)
+{
+    return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
 }
 
-/* filter the vertical edge between packed words l (4 px left) and r (4 px right) */
-__device__ __forceinline__ void vedge(unsigned &l, unsigned &r, bool mbedge, bool simple, const LfParams &P)
+template <bool MB>
+__device__ __forceinline__ void edge8(int &p3, int &p2, int &p1, int &p0, int &q0, int &q1, int &q2, int &q3,
+                                      bool simple, const LfParams &P)
 {
-    int p3, p2, p1, p0, q0, q1, q2, q3;
-    unpack(l, p3, p2, p1, p0);
-    unpack(r, q0, q1, q2, q3);
-    if (simple) lf_simple(p1, p0, q0, q1, mbedge ? P.mblim : P.blim);
-    else if (mbedge) lf_mbedge(p3, p2, p1, p0, q0, q1, q2, q3, P);
+    if (simple) lf_simple(p1, p0, q0, q1, MB ? P.mblim : P.blim);
+    else if (MB) lf_mbedge(p3, p2, p1, p0, q0, q1, q2, q3, P);
     else lf_inner(p3, p2, p1, p0, q0, q1, q2, q3, P);
-    l = pack4(p3, p2, p1, p0);
-    r = pack4(q0, q1, q2, q3);
 }
 
-/* filter the horizontal edge between v[i-4..i-1] and v[i..i+3] of a pixel column */
-template <int N>
-__device__ __forceinline__ void hedge(int (&v)[N], int i, bool mbedge, bool simple, const LfParams &P)
+/* ---- global hand-off (across CTAs) ------------------------------------------------------ */
+__device__ __forceinline__ void st_msg2(uint8_t *p, unsigned a, unsigned b, unsigned tag)
 {
-    if (simple) lf_simple(v[i - 2], v[i - 1], v[i], v[i + 1], mbedge ? P.mblim : P.blim);
-    else if (mbedge) lf_mbedge(v[i - 4], v[i - 3], v[i - 2], v[i - 1], v[i], v[i + 1], v[i + 2], v[i + 3], P);
-    else lf_inner(v[i - 4], v[i - 3], v[i - 2], v[i - 1], v[i], v[i + 1], v[i + 2], v[i + 3], P);
+    unsigned long long x = ((unsigned long long)tag << 32) | a, y = ((unsigned long long)tag << 32) | b;
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(x), "l"(y) : "memory");
+}
+__device__ __forceinline__ void ld_msg2(const uint8_t *p, unsigned long long &x, unsigned long long &y)
+{
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "l"(p) : "memory");
+}
+/* slot: 256 B per MB = luma rows 12..15 (4 x 32 B), U rows 4..7 (4 x 16 B), V rows 4..7 */
+__device__ __forceinline__ void g_send(uint8_t *slot, const unsigned (&m)[4], unsigned tag, bool luma)
+{
+    if (luma) { st_msg2(slot, m[0], m[1], tag); st_msg2(slot + 16, m[2], m[3], tag); }
+    else st_msg2(slot, m[0], m[1], tag);
+}
+__device__ __forceinline__ void g_recv(const uint8_t *slot, unsigned (&m)[4], unsigned tag, bool luma)
+{
+    unsigned long long a, b, c = 0, d = 0;
+    for (;;) {
+        ld_msg2(slot, a, b);
+        if (luma) ld_msg2(slot + 16, c, d);
+        bool ok = (unsigned)(a >> 32) == tag && (unsigned)(b >> 32) == tag;
+        if (luma) ok = ok && (unsigned)(c >> 32) == tag && (unsigned)(d >> 32) == tag;
+        if (ok) break;
+        __nanosleep(200);
+    }
+    m[0] = (unsigned)a; m[1] = (unsigned)b; m[2] = (unsigned)c; m[3] = (unsigned)d;
 }
 
-__global__ void __launch_bounds__(LF_ROWS_PER_CTA * 32)
+__global__ void __launch_bounds__(LF_ROWS_PER_CTA * 32, 8)
 k_loopfilter(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g,
              unsigned *ticket, const unsigned ticket_base)
 {
@@ -130,7 +148,11 @@ k_loopfilter(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g,
     __shared__ unsigned s_ticket;
     __shared__ uint8_t s_lvl[64];                          /* [seg][ref][mode class] */
     __shared__ __align__(16) uint8_t s_tile[LF_ROWS_PER_CTA][512];
+    /* message ring of row w -> row w+1: 128 B = luma rows 12..15 (4x16), U 4..7 (4x8), V 4..7 */
+    __shared__ __align__(16) uint8_t s_ring[LF_ROWS_PER_CTA][LF_RING][128];
+    __shared__ volatile unsigned s_sent[LF_ROWS_PER_CTA], s_rcvd[LF_ROWS_PER_CTA];
     if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u) - ticket_base;
+    if (threadIdx.x < LF_ROWS_PER_CTA) { s_sent[threadIdx.x] = 0; s_rcvd[threadIdx.x] = 0; }
     __syncthreads();
     const unsigned t = s_ticket;
     const int ji = t % n_jobs, group = t / n_jobs;
@@ -163,9 +185,7 @@ k_loopfilter(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g,
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mb_row = group * LF_ROWS_PER_CTA + warp;
     if (mb_row >= g.mb_rows) return;
-    const unsigned base = job.epoch_lf << VP8B200_EPOCH_SHIFT;
-    unsigned *my_prog = job.progress + g.mb_rows + mb_row;
-    const unsigned *up_prog = my_prog - 1;
+    const unsigned tag = job.epoch_lf;                     /* marks this frame's global messages */
     const bool simple = h.filter_type != 0;
     const bool key = h.frame_type == 0;
     const int sharp = h.sharpness_level;
@@ -180,15 +200,51 @@ k_loopfilter(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g,
     const bool lane_on = luma || !simple;                  /* simple filter: luma only */
     uint8_t *tile = s_tile[warp] + (luma ? 0 : (lane < 24 ? 320 : 416));
     const bool top = mb_row > 0;
+    const bool last_row = mb_row == g.mb_rows - 1;
+    /* rows >= keep of every MB (not in the last MB row) are finished and stored by the row
+     * below; this row hands rows keep.. down as a message instead */
+    const int keep = luma ? 12 : 4;
+    const bool owns_store = lane_on && (last_row || pi <= keep);
+    const bool sender = lane_on && !last_row && pi >= keep;
+    const bool receiver = lane_on && top && pi < 4;
+    const bool send_smem = warp < LF_ROWS_PER_CTA - 1;     /* consumer row lives in this CTA */
+    const bool recv_smem = warp > 0;
+    /* global slot offsets */
+    const int gs_off = luma ? (pi - 12) * 32 : (lane < 24 ? 128 : 192) + (pi - 4) * 16;
+    const int gr_off = luma ? pi * 32 : (lane < 24 ? 128 : 192) + pi * 16;
+    uint8_t *gmsg_out = job.lf_msg + (size_t)mb_row * g.mb_cols * 256 + gs_off;
+    const uint8_t *gmsg_in = job.lf_msg + (size_t)(mb_row - 1) * g.mb_cols * 256 + gr_off;
+    /* shared ring offsets */
+    const int ss_off = luma ? (pi - 12) * 16 : (lane < 24 ? 64 : 96) + (pi - 4) * 8;
+    const int sr_off = luma ? pi * 16 : (lane < 24 ? 64 : 96) + pi * 8;
 
     const unsigned *mbrec = reinterpret_cast<const unsigned *>(job.mb + (size_t)mb_row * g.mb_cols);
-    unsigned cur[4] = {0, 0, 0, 0}, nxt[4] = {0, 0, 0, 0}, halo = 0;
+    unsigned cur[4] = {0, 0, 0, 0}, nxt[4] = {0, 0, 0, 0}, prev[3] = {0, 0, 0}, halo = 0;
     if (lane_on) {
         if (luma) { uint4 v = *reinterpret_cast<const uint4 *>(rowp); cur[0] = v.x; cur[1] = v.y; cur[2] = v.z; cur[3] = v.w; }
         else { uint2 v = *reinterpret_cast<const uint2 *>(rowp); cur[0] = v.x; cur[1] = v.y; }
     }
     unsigned rec = mbrec[0], rec_n = 0;
-    unsigned seen = base;                                  /* last value read from up_prog */
+
+    /* message for MB `col` of this row: words of rows keep.. after the next MB's left edge */
+    auto send = [&](int col) {
+        unsigned m[4];
+        if (luma) { m[0] = prev[0]; m[1] = prev[1]; m[2] = prev[2]; m[3] = halo; }
+        else { m[0] = prev[0]; m[1] = halo; m[2] = 0; m[3] = 0; }
+        if (send_smem) {
+            while ((int)(col - s_rcvd[warp]) >= LF_RING) { }             /* ring full: wait for the consumer */
+            if (sender) {
+                uint8_t *slot = s_ring[warp][col & (LF_RING - 1)] + ss_off;
+                if (luma) *reinterpret_cast<uint4 *>(slot) = make_uint4(m[0], m[1], m[2], m[3]);
+                else *reinterpret_cast<uint2 *>(slot) = make_uint2(m[0], m[1]);
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) s_sent[warp] = (unsigned)col + 1;
+        } else if (sender) {
+            g_send(gmsg_out + (size_t)col * 256, m, tag, luma);
+        }
+    };
 
     for (int c = 0; c < g.mb_cols; c++) {
         /* prefetch the next macroblock's rows and record */
@@ -207,114 +263,151 @@ k_loopfilter(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g,
                          : (y_mode <= VP8B200_TM_PRED || y_mode == VP8B200_ZEROMV) ? 1 : 2;
         const int level = s_lvl[((flags & 3) << 4) | (ref << 2) | mclass];
         uint8_t *colp = rowp + c * mbw;                     /* my row at this MB's x = 0 */
-
-        if (level == 0) {
-            /* untouched macroblock: pass the pixels through */
-            if (lane_on) {
-                if (c > 0) *reinterpret_cast<unsigned *>(colp - 4) = halo;
-                if (luma) { *reinterpret_cast<unsigned *>(colp) = cur[0]; *reinterpret_cast<unsigned *>(colp + 4) = cur[1];
-                            *reinterpret_cast<unsigned *>(colp + 8) = cur[2]; halo = cur[3]; }
-                else { *reinterpret_cast<unsigned *>(colp) = cur[0]; halo = cur[1]; }
+        LfParams P;
+        {   /* loopfilter.c:66-96 and :28-50 */
+            int il = level >> (sharp > 0);
+            il >>= (sharp > 4);
+            if (sharp > 0) il = min(il, 9 - sharp);
+            il = max(il, 1);
+            P.ilim = il; P.blim = 2 * level + il; P.mblim = 2 * (level + 2) + il;
+            P.thr = key ? (level >= 40 ? 2 : (level >= 15 ? 1 : 0))
+                        : (level >= 40 ? 3 : (level >= 20 ? 2 : (level >= 15 ? 1 : 0)));
+        }
+        /* ---- vertical edges, lane = pixel row, pixels unpacked once ---- */
+        if (lane_on && level) {
+            int x[8];
+            if (c > 0) {
+                int h0, h1, h2, h3;
+                unpack(halo, h0, h1, h2, h3);
+                unpack(cur[0], x[0], x[1], x[2], x[3]);
+                edge8<true>(h0, h1, h2, h3, x[0], x[1], x[2], x[3], simple, P);
+                halo = pack(h0, h1, h2, h3);
+                if (skip_lf) cur[0] = pack(x[0], x[1], x[2], x[3]);
+            } else if (!skip_lf) {
+                unpack(cur[0], x[0], x[1], x[2], x[3]);
             }
-        } else {
-            LfParams P;
-            {   /* loopfilter.c:66-96 and :28-50 */
-                int il = level >> (sharp > 0);
-                il >>= (sharp > 4);
-                if (sharp > 0) il = min(il, 9 - sharp);
-                il = max(il, 1);
-                P.ilim = il; P.blim = 2 * level + il; P.mblim = 2 * (level + 2) + il;
-                P.thr = key ? (level >= 40 ? 2 : (level >= 15 ? 1 : 0))
-                            : (level >= 40 ? 3 : (level >= 20 ? 2 : (level >= 15 ? 1 : 0)));
-            }
-            /* ---- vertical edges, lane = pixel row ---- */
-            if (lane_on) {
-                if (c > 0) vedge(halo, cur[0], true, simple, P);
-                if (!skip_lf) {
-                    vedge(cur[0], cur[1], false, simple, P);
-                    if (luma) { vedge(cur[1], cur[2], false, simple, P); vedge(cur[2], cur[3], false, simple, P); }
+            if (!skip_lf) {
+                unpack(cur[1], x[4], x[5], x[6], x[7]);
+                edge8<false>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7], simple, P);
+                cur[0] = pack(x[0], x[1], x[2], x[3]);
+                if (luma) {
+                    int y[8];
+                    unpack(cur[2], y[0], y[1], y[2], y[3]);
+                    edge8<false>(x[4], x[5], x[6], x[7], y[0], y[1], y[2], y[3], simple, P);
+                    cur[1] = pack(x[4], x[5], x[6], x[7]);
+                    unpack(cur[3], y[4], y[5], y[6], y[7]);
+                    edge8<false>(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7], simple, P);
+                    cur[2] = pack(y[0], y[1], y[2], y[3]);
+                    cur[3] = pack(y[4], y[5], y[6], y[7]);
+                } else {
+                    cur[1] = pack(x[4], x[5], x[6], x[7]);
                 }
-                if (c > 0) *reinterpret_cast<unsigned *>(colp - 4) = halo;
-                /* rows into the tile (rows 4.. of the tile = rows 0.. of the MB) */
+            }
+        }
+        /* the previous MB of this row is now final: store / hand down its last 4 columns */
+        if (c > 0) {
+            if (owns_store) *reinterpret_cast<unsigned *>(colp - 4) = halo;
+            if (!last_row) send(c - 1);
+        }
+        /* ---- the 4 rows above arrive as a message from the row above ---- */
+        if (top) {
+            if (recv_smem) {
+                while (s_sent[warp - 1] <= (unsigned)c) { }
+                __threadfence_block();
+                if (receiver) {
+                    const uint8_t *slot = s_ring[warp - 1][c & (LF_RING - 1)] + sr_off;
+                    if (luma) *reinterpret_cast<uint4 *>(tile + pi * 16) = *reinterpret_cast<const uint4 *>(slot);
+                    else *reinterpret_cast<uint2 *>(tile + pi * 8) = *reinterpret_cast<const uint2 *>(slot);
+                }
+                __syncwarp();
+                if (lane == 0) s_rcvd[warp - 1] = (unsigned)c + 1;
+            } else if (receiver) {
+                unsigned m[4];
+                g_recv(gmsg_in + (size_t)c * 256, m, tag, luma);
+                if (luma) *reinterpret_cast<uint4 *>(tile + pi * 16) = make_uint4(m[0], m[1], m[2], m[3]);
+                else *reinterpret_cast<uint2 *>(tile + pi * 8) = make_uint2(m[0], m[1]);
+            }
+        }
+        if (level) {
+            /* rows the horizontal edges touch: all of them, or only rows 0..3 for the top edge
+             * of a macroblock without inner edges (nothing at all if that has no top either) */
+            const int nrows = skip_lf ? 4 : mbw;            /* MB rows entering the tile */
+            if (lane_on && (!skip_lf || top) && pi < nrows) {
                 if (luma) *reinterpret_cast<uint4 *>(tile + (pi + 4) * 16) = make_uint4(cur[0], cur[1], cur[2], cur[3]);
                 else *reinterpret_cast<uint2 *>(tile + (pi + 4) * 8) = make_uint2(cur[0], cur[1]);
             }
-            /* ---- the 4 rows above, once the row above is far enough ---- */
-            if (top) {
-                /* row above must have finished iteration c+1 (which stores the last 4
-                 * columns of its MB c); for the last column that is its end-of-row flush,
-                 * published as mb_cols+1.  The counter is re-read only when the value seen
-                 * last time is not enough (the row above is usually several MBs ahead);
-                 * lane 0 polls, the acquire is extended to the warp by __syncwarp. */
-                const unsigned need = base + (unsigned)(c + 2);
-                if ((int)(seen - need) < 0) {
-                    if (lane == 0) {
-                        unsigned v = lf_ld_acquire(up_prog);
-                        while ((int)(v - need) < 0) { __nanosleep(40); v = lf_ld_acquire(up_prog); }
-                        seen = v;
-                    }
-                    seen = __shfl_sync(FULL_MASK, seen, 0);
-                    __syncwarp();                  /* order every lane's loads after the acquire */
-                }
-                if (lane_on && pi < 4) {
-                    const uint8_t *ap = plane + (size_t)(mb_row * mbw - 4 + pi) * stride + c * mbw;
-                    if (luma) *reinterpret_cast<uint4 *>(tile + pi * 16) = __ldcg(reinterpret_cast<const uint4 *>(ap));
-                    else *reinterpret_cast<uint2 *>(tile + pi * 8) = __ldcg(reinterpret_cast<const uint2 *>(ap));
-                }
-            }
             __syncwarp();
             /* ---- horizontal edges, lane = pixel column ---- */
-            if (lane_on) {
-                if (luma) {
-                    int v[20];
+            if (lane_on && (!skip_lf || top)) {
+                int v[8];
+                if (top) {
 #pragma unroll
-                    for (int r = 0; r < 20; r++) v[r] = (r >= 4 || top) ? tile[r * 16 + pi] : 0;
-                    if (top) hedge(v, 4, true, simple, P);
-                    if (!skip_lf) { hedge(v, 8, false, simple, P); hedge(v, 12, false, simple, P); hedge(v, 16, false, simple, P); }
+                    for (int r = 0; r < 8; r++) v[r] = tile[r * mbw + pi];
+                    edge8<true>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], simple, P);
 #pragma unroll
-                    for (int r = 1; r < 20; r++) if (r >= 4 || top) tile[r * 16 + pi] = (uint8_t)v[r];
+                    for (int r = 1; r < 4; r++) tile[r * mbw + pi] = (uint8_t)v[r];
+                    if (skip_lf) {
+#pragma unroll
+                        for (int r = 4; r < 7; r++) tile[r * mbw + pi] = (uint8_t)v[r];
+                    }
                 } else {
-                    int v[12];
 #pragma unroll
-                    for (int r = 0; r < 12; r++) v[r] = (r >= 4 || top) ? tile[r * 8 + pi] : 0;
-                    if (top) hedge(v, 4, true, simple, P);
-                    if (!skip_lf) hedge(v, 8, false, simple, P);
+                    for (int r = 4; r < 8; r++) v[r] = tile[r * mbw + pi];
+                }
+                if (!skip_lf) {
+                    int w[8];
 #pragma unroll
-                    for (int r = 1; r < 12; r++) if (r >= 4 || top) tile[r * 8 + pi] = (uint8_t)v[r];
+                    for (int r = 0; r < 4; r++) w[r] = tile[(r + 8) * mbw + pi];
+                    edge8<false>(v[4], v[5], v[6], v[7], w[0], w[1], w[2], w[3], simple, P);
+#pragma unroll
+                    for (int r = 4; r < 8; r++) tile[r * mbw + pi] = (uint8_t)v[r];
+                    if (luma) {
+#pragma unroll
+                        for (int r = 4; r < 8; r++) w[r] = tile[(r + 8) * mbw + pi];
+                        edge8<false>(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], simple, P);
+#pragma unroll
+                        for (int r = 0; r < 4; r++) tile[(r + 8) * mbw + pi] = (uint8_t)w[r];
+#pragma unroll
+                        for (int r = 0; r < 4; r++) v[r] = tile[(r + 16) * mbw + pi];
+                        edge8<false>(w[4], w[5], w[6], w[7], v[0], v[1], v[2], v[3], simple, P);
+#pragma unroll
+                        for (int r = 4; r < 8; r++) tile[(r + 8) * mbw + pi] = (uint8_t)w[r];
+#pragma unroll
+                        for (int r = 0; r < 4; r++) tile[(r + 16) * mbw + pi] = (uint8_t)v[r];
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 4; r++) tile[(r + 8) * mbw + pi] = (uint8_t)w[r];
+                    }
                 }
             }
             __syncwarp();
-            /* ---- rows back out; the last word waits for the next MB's left edge ---- */
-            if (lane_on) {
-                if (luma) {
-                    uint4 v = *reinterpret_cast<const uint4 *>(tile + (pi + 4) * 16);
-                    *reinterpret_cast<unsigned *>(colp) = v.x; *reinterpret_cast<unsigned *>(colp + 4) = v.y;
-                    *reinterpret_cast<unsigned *>(colp + 8) = v.z; halo = v.w;
-                } else {
-                    uint2 v = *reinterpret_cast<const uint2 *>(tile + (pi + 4) * 8);
-                    *reinterpret_cast<unsigned *>(colp) = v.x; halo = v.y;
-                }
-                if (top && pi >= 1 && pi < 4) {             /* rows -3..-1 of the MB above */
-                    uint8_t *ap = plane + (size_t)(mb_row * mbw - 4 + pi) * stride + c * mbw;
-                    if (luma) *reinterpret_cast<uint4 *>(ap) = *reinterpret_cast<const uint4 *>(tile + pi * 16);
-                    else *reinterpret_cast<uint2 *>(ap) = *reinterpret_cast<const uint2 *>(tile + pi * 8);
-                }
+            if (lane_on && (!skip_lf || top) && pi < nrows) {
+                if (luma) { uint4 v = *reinterpret_cast<const uint4 *>(tile + (pi + 4) * 16); cur[0] = v.x; cur[1] = v.y; cur[2] = v.z; cur[3] = v.w; }
+                else { uint2 v = *reinterpret_cast<const uint2 *>(tile + (pi + 4) * 8); cur[0] = v.x; cur[1] = v.y; }
             }
-            __syncwarp();
+        } else {
+            __syncwarp();                                   /* message rows visible in the tile */
         }
-        /* publish: columns < c are final for the row below once c+1 is published.  One
-         * release by lane 0 after the warp barrier covers every lane's stores (the barrier
-         * orders them before the release; release is cumulative). */
-        __syncwarp();
-        if (lane == 0) lf_st_release(my_prog, base + c + 1);
+        /* ---- rows out; the last word waits for the next MB's left edge ---- */
+        if (owns_store) {
+            *reinterpret_cast<unsigned *>(colp) = cur[0];
+            if (luma) { *reinterpret_cast<unsigned *>(colp + 4) = cur[1]; *reinterpret_cast<unsigned *>(colp + 8) = cur[2]; }
+        }
+        if (receiver && pi >= 1) {                          /* rows -3..-1: this row finishes them */
+            uint8_t *ap = plane + (size_t)(mb_row * mbw - 4 + pi) * stride + c * mbw;
+            if (luma) *reinterpret_cast<uint4 *>(ap) = *reinterpret_cast<const uint4 *>(tile + pi * 16);
+            else *reinterpret_cast<uint2 *>(ap) = *reinterpret_cast<const uint2 *>(tile + pi * 8);
+        }
+        if (luma) { prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2]; halo = cur[3]; }
+        else { prev[0] = cur[0]; halo = cur[1]; }
+        __syncwarp();                                       /* tile is reused by the next MB */
         rec = rec_n;
 #pragma unroll
         for (int i = 0; i < 4; i++) cur[i] = nxt[i];
     }
     /* last 4 columns of the row */
-    if (lane_on) *reinterpret_cast<unsigned *>(rowp + g.mb_cols * mbw - 4) = halo;
-    __syncwarp();
-    if (lane == 0) lf_st_release(my_prog, base + g.mb_cols + 1);
+    if (owns_store) *reinterpret_cast<unsigned *>(rowp + g.mb_cols * mbw - 4) = halo;
+    if (!last_row) send(g.mb_cols - 1);
 }
 
 void vp8b200_launch_loopfilter(cudaStream_t s, const FrameJob *jobs, int n_jobs, const Geo &g,

@@ -55,6 +55,7 @@ struct vp8b200_ctx {
     bool open;
     vp8b200_frame_hdr cur_hdr;
     unsigned *d_progress;          /* 2*mb_rows wavefront counters */
+    uint8_t *d_lfmsg;              /* loop-filter row hand-off messages, 256 B per MB */
     unsigned *d_tickets;           /* [0] intra, [1] loop filter */
     unsigned ticket_base[2];
     unsigned epoch_intra, epoch_lf;
@@ -129,7 +130,7 @@ static void free_ctx(vp8b200_ctx *c)
         cudaFreeHost(c->h_bjobs[i]); cudaFree(c->d_bjobs[i]);
         if (c->bjobs_done[i]) cudaEventDestroy(c->bjobs_done[i]);
     }
-    cudaFree(c->d_progress); cudaFree(c->d_tickets);
+    cudaFree(c->d_progress); cudaFree(c->d_tickets); cudaFree(c->d_lfmsg);
     if (c->fetch_done) cudaEventDestroy(c->fetch_done);
     if (c->spans) {
         for (auto &sp : *c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -167,6 +168,8 @@ static int create_impl(vp8b200_ctx *c)
     for (int i = 0; i < NBJOB; i++) CK(c, cudaEventCreateWithFlags(&c->bjobs_done[i], cudaEventDisableTiming));
     CK(c, cudaMalloc((void **)&c->d_progress, 2 * g.mb_rows * sizeof(unsigned)));
     CK(c, cudaMemsetAsync(c->d_progress, 0, 2 * g.mb_rows * sizeof(unsigned), c->stream));
+    CK(c, cudaMalloc((void **)&c->d_lfmsg, (size_t)c->n_mb * 256));
+    CK(c, cudaMemsetAsync(c->d_lfmsg, 0, (size_t)c->n_mb * 256, c->stream));
     CK(c, cudaMalloc((void **)&c->d_tickets, 2 * sizeof(unsigned)));
     CK(c, cudaMemsetAsync(c->d_tickets, 0, 2 * sizeof(unsigned), c->stream));
     {
@@ -300,6 +303,7 @@ static void fill_job(vp8b200_ctx *c, FrameJob *j, const vp8b200_frame_hdr &h, co
     j->ref[1] = c->fb[h.fb_last]; j->ref[2] = c->fb[h.fb_golden]; j->ref[3] = c->fb[h.fb_altref];
     j->mb = d_mb; j->aux = d_aux; j->coef = d_coef;
     j->progress = c->d_progress;
+    j->lf_msg = c->d_lfmsg;
     if (run_intra) c->epoch_intra++;
     if (run_lf) c->epoch_lf++;
     j->epoch_intra = c->epoch_intra;

@@ -23,7 +23,8 @@ struct FrameJob {
     const vp8b200_mb *mb;
     const vp8b200_aux *aux;
     const int16_t *coef;
-    unsigned int *progress;       /* [0,mb_rows): intra wavefront, [mb_rows,2*mb_rows): LF    */
+    unsigned int *progress;       /* [0,mb_rows): intra wavefront progress counters           */
+    uint8_t *lf_msg;              /* loop-filter row hand-off: 256 B per macroblock           */
     unsigned int epoch_intra;     /* progress values of this frame are (epoch << 13) + columns; */
     unsigned int epoch_lf;        /* each counter advances only when its kernel really runs     */
     unsigned int n_intra;         /* intra macroblocks in the frame (0 => intra kernel idle)  */
