@@ -1,0 +1,309 @@
+/* kernels_intra.cu - intra prediction + residual for the intra macroblocks of a frame.
+ *
+ * Restates vp8_build_intra_predictors_mby_s / mbuv_s (vp8/common/reconintra.c:139-263,
+ * :403-546), vp8_intra4x4_predict (reconintra4x4.c:16-296) with its above-right rule
+ * (vp8_intra_prediction_down_copy, :305-317), the 127/129 frame-edge rule of
+ * vp8_setup_intra_recon (setupintrarecon.c:15-32), the right-edge rule of vp8_extend_mb_row
+ * (extend.c:160-185) and the residual add of decodframe.c:192-304.
+ *
+ * Intra prediction reads the UNFILTERED reconstruction of the left, above-left, above and
+ * above-right neighbours, so intra macroblocks form a wavefront.  One warp owns one intra
+ * macroblock.  The host hands over the list of intra MBs sorted by wavefront index c + 2r
+ * (all of them on key frames, a handful on P frames, where inter MBs were already finished by
+ * k_inter); warps take list entries through an atomic ticket in that order, so every
+ * dependency belongs to an earlier ticket, i.e. to a warp that is already running: no
+ * deadlock, and no reliance on block scheduling order.  A warp waits only for those of its
+ * four neighbours that are themselves intra (per-MB done flags, release/acquire).
+ *
+ * Inside a macroblock: borders are gathered into a shared-memory tile (frame-edge values are
+ * synthesised, never read from the frame), residuals of all blocks are computed first
+ * (lane = 4x4 block; they do not depend on prediction), whole-block modes predict with
+ * lane = block, and B_PRED runs its 16 sub-blocks as a 10-step anti-diagonal wavefront with
+ * lane = PIXEL (two sub-blocks x 16 pixels per step) driven by a constant-memory table that
+ * encodes every directional predictor as a 3-tap or 2-tap average of the edge array.
+ */
+#include "vp8b200_dev.cuh"
+
+#define INTRA_WARPS 4
+#define YS 48             /* luma tile pitch: rows -1..15, cols -16..31 ; index (r+1)*48 + 16 + c */
+#define CS 16             /* chroma tile pitch: rows -1..7, cols -4..11 ; index (r+1)*16 + 4 + c  */
+
+/* B_PRED predictor table: [mode][pixel] = i0 | i1<<4 | i2<<8 | kind<<12 over the edge array
+ * E[0..3] = L3 L2 L1 L0, E[4] = top-left, E[5..12] = A0..A7.
+ * kind 0: (E[i0] + 2 E[i1] + E[i2] + 2) >> 2 ; 1: (E[i0] + E[i1] + 1) >> 1 ; 2: DC ; 3: TM */
+__constant__ unsigned short c_bpred[10][16];
+
+static unsigned short ent(int kind, int a, int b, int c) { return (unsigned short)(a | (b << 4) | (c << 8) | (kind << 12)); }
+
+void vp8b200_upload_intra_constants()
+{
+    unsigned short t[10][16];
+    auto A3 = [](int a, int b, int c) { return ent(0, a, b, c); };
+    auto A2 = [](int a, int b) { return ent(1, a, b, 0); };
+    for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) {
+            const int p = r * 4 + c;
+            t[VP8B200_B_DC_PRED][p] = ent(2, 0, 0, 0);
+            t[VP8B200_B_TM_PRED][p] = ent(3, 0, 0, 0);
+            t[VP8B200_B_VE_PRED][p] = A3(4 + c, 5 + c, 6 + c);
+            /* rows: (tl,L0,L1) (L0,L1,L2) (L1,L2,L3) (L2,L3,L3) with L_k = E[3-k] */
+            t[VP8B200_B_HE_PRED][p] = r == 0 ? A3(4, 3, 2) : r == 1 ? A3(3, 2, 1) : r == 2 ? A3(2, 1, 0) : A3(1, 0, 0);
+            { int k = r + c; t[VP8B200_B_LD_PRED][p] = k < 6 ? A3(5 + k, 6 + k, 7 + k) : A3(11, 12, 12); }
+            { int k = 3 - r + c; t[VP8B200_B_RD_PRED][p] = A3(k, k + 1, k + 2); }
+        }
+#define S(m, r, c, v) t[m][(r) * 4 + (c)] = (v)
+    /* reconintra4x4.c:178-210 (VR), E = pp */
+    S(VP8B200_B_VR_PRED, 3, 0, A3(1, 2, 3)); S(VP8B200_B_VR_PRED, 2, 0, A3(2, 3, 4));
+    S(VP8B200_B_VR_PRED, 3, 1, A3(3, 4, 5)); S(VP8B200_B_VR_PRED, 1, 0, A3(3, 4, 5));
+    S(VP8B200_B_VR_PRED, 2, 1, A2(4, 5));    S(VP8B200_B_VR_PRED, 0, 0, A2(4, 5));
+    S(VP8B200_B_VR_PRED, 3, 2, A3(4, 5, 6)); S(VP8B200_B_VR_PRED, 1, 1, A3(4, 5, 6));
+    S(VP8B200_B_VR_PRED, 2, 2, A2(5, 6));    S(VP8B200_B_VR_PRED, 0, 1, A2(5, 6));
+    S(VP8B200_B_VR_PRED, 3, 3, A3(5, 6, 7)); S(VP8B200_B_VR_PRED, 1, 2, A3(5, 6, 7));
+    S(VP8B200_B_VR_PRED, 2, 3, A2(6, 7));    S(VP8B200_B_VR_PRED, 0, 2, A2(6, 7));
+    S(VP8B200_B_VR_PRED, 1, 3, A3(6, 7, 8)); S(VP8B200_B_VR_PRED, 0, 3, A2(7, 8));
+    /* :212-240 (VL), pp = Above -> E[5 + i] */
+    S(VP8B200_B_VL_PRED, 0, 0, A2(5, 6));     S(VP8B200_B_VL_PRED, 1, 0, A3(5, 6, 7));
+    S(VP8B200_B_VL_PRED, 2, 0, A2(6, 7));     S(VP8B200_B_VL_PRED, 0, 1, A2(6, 7));
+    S(VP8B200_B_VL_PRED, 1, 1, A3(6, 7, 8));  S(VP8B200_B_VL_PRED, 3, 0, A3(6, 7, 8));
+    S(VP8B200_B_VL_PRED, 2, 1, A2(7, 8));     S(VP8B200_B_VL_PRED, 0, 2, A2(7, 8));
+    S(VP8B200_B_VL_PRED, 3, 1, A3(7, 8, 9));  S(VP8B200_B_VL_PRED, 1, 2, A3(7, 8, 9));
+    S(VP8B200_B_VL_PRED, 0, 3, A2(8, 9));     S(VP8B200_B_VL_PRED, 2, 2, A2(8, 9));
+    S(VP8B200_B_VL_PRED, 1, 3, A3(8, 9, 10)); S(VP8B200_B_VL_PRED, 3, 2, A3(8, 9, 10));
+    S(VP8B200_B_VL_PRED, 2, 3, A3(9, 10, 11)); S(VP8B200_B_VL_PRED, 3, 3, A3(10, 11, 12));
+    /* :242-276 (HD), E = pp */
+    S(VP8B200_B_HD_PRED, 3, 0, A2(0, 1));    S(VP8B200_B_HD_PRED, 3, 1, A3(0, 1, 2));
+    S(VP8B200_B_HD_PRED, 2, 0, A2(1, 2));    S(VP8B200_B_HD_PRED, 3, 2, A2(1, 2));
+    S(VP8B200_B_HD_PRED, 2, 1, A3(1, 2, 3)); S(VP8B200_B_HD_PRED, 3, 3, A3(1, 2, 3));
+    S(VP8B200_B_HD_PRED, 2, 2, A2(2, 3));    S(VP8B200_B_HD_PRED, 1, 0, A2(2, 3));
+    S(VP8B200_B_HD_PRED, 2, 3, A3(2, 3, 4)); S(VP8B200_B_HD_PRED, 1, 1, A3(2, 3, 4));
+    S(VP8B200_B_HD_PRED, 1, 2, A2(3, 4));    S(VP8B200_B_HD_PRED, 0, 0, A2(3, 4));
+    S(VP8B200_B_HD_PRED, 1, 3, A3(3, 4, 5)); S(VP8B200_B_HD_PRED, 0, 1, A3(3, 4, 5));
+    S(VP8B200_B_HD_PRED, 0, 2, A3(4, 5, 6)); S(VP8B200_B_HD_PRED, 0, 3, A3(5, 6, 7));
+    /* :278-294 (HU), pp = Left: L_k = E[3-k] */
+    S(VP8B200_B_HU_PRED, 0, 0, A2(3, 2));    S(VP8B200_B_HU_PRED, 0, 1, A3(3, 2, 1));
+    S(VP8B200_B_HU_PRED, 0, 2, A2(2, 1));    S(VP8B200_B_HU_PRED, 1, 0, A2(2, 1));
+    S(VP8B200_B_HU_PRED, 0, 3, A3(2, 1, 0)); S(VP8B200_B_HU_PRED, 1, 1, A3(2, 1, 0));
+    S(VP8B200_B_HU_PRED, 1, 2, A2(1, 0));    S(VP8B200_B_HU_PRED, 2, 0, A2(1, 0));
+    S(VP8B200_B_HU_PRED, 1, 3, A3(1, 0, 0)); S(VP8B200_B_HU_PRED, 2, 1, A3(1, 0, 0));
+    S(VP8B200_B_HU_PRED, 2, 2, A3(0, 0, 0)); S(VP8B200_B_HU_PRED, 2, 3, A3(0, 0, 0));
+    S(VP8B200_B_HU_PRED, 3, 0, A3(0, 0, 0)); S(VP8B200_B_HU_PRED, 3, 1, A3(0, 0, 0));
+    S(VP8B200_B_HU_PRED, 3, 2, A3(0, 0, 0)); S(VP8B200_B_HU_PRED, 3, 3, A3(0, 0, 0));
+#undef S
+    cudaMemcpyToSymbol(c_bpred, t, sizeof t);
+}
+
+/* whole-block modes (reconintra.c:139-263, :403-546) for the lane's 4x4 block at (bx, by);
+ * T points at tile pixel (0,0) with pitch ts; dc is the precomputed DC value */
+__device__ __forceinline__ void block_mode(int mode, const uint8_t *T, int ts, int bx, int by, int dc, unsigned (&px)[4])
+{
+    const uint8_t *above = T - ts;
+    if (mode == VP8B200_DC_PRED) {
+        const unsigned v = (unsigned)dc * 0x01010101u;
+#pragma unroll
+        for (int r = 0; r < 4; r++) px[r] = v;
+    } else if (mode == VP8B200_V_PRED) {
+        const unsigned v = *reinterpret_cast<const unsigned *>(above + bx);
+#pragma unroll
+        for (int r = 0; r < 4; r++) px[r] = v;
+    } else if (mode == VP8B200_H_PRED) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) px[r] = (unsigned)T[(by + r) * ts - 1] * 0x01010101u;
+    } else { /* TM_PRED */
+        const int tl = above[-1];
+        int a[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) a[c] = above[bx + c] - tl;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int l = T[(by + r) * ts - 1];
+            px[r] = pack4(clamp255(l + a[0]), clamp255(l + a[1]), clamp255(l + a[2]), clamp255(l + a[3]));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(INTRA_WARPS * 32)
+k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const unsigned max_intra,
+        unsigned *ticket, const unsigned ticket_base)
+{
+    __shared__ FrameJob s_job[INTRA_WARPS];
+    __shared__ unsigned s_ticket;
+    __shared__ __align__(16) uint8_t s_yt[INTRA_WARPS][17 * YS];
+    __shared__ __align__(16) uint8_t s_ct[INTRA_WARPS][2][9 * CS];
+    __shared__ __align__(16) short s_res[INTRA_WARPS][16][16];
+    if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u) - ticket_base;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned t = s_ticket * INTRA_WARPS + warp;
+    const int ji = t % n_jobs;
+    const unsigned k = t / n_jobs;
+    if (k >= max_intra) return;
+    FrameJob &job = s_job[warp];
+    {
+        const unsigned *s = reinterpret_cast<const unsigned *>(&jobs[ji]);
+        unsigned *d = reinterpret_cast<unsigned *>(&job);
+        for (int i = lane; i < (int)(sizeof(FrameJob) / 4); i += 32) d[i] = s[i];
+    }
+    __syncwarp();
+    if (k >= job.n_intra) return;
+    const unsigned epoch = job.epoch_intra;
+    const int mbi = (int)job.intra_list[k];
+    const int mb_row = mbi / g.mb_cols, mb_col = mbi - mb_row * g.mb_cols;
+    vp8b200_mb mb;
+    *reinterpret_cast<uint4 *>(&mb) = __ldg(reinterpret_cast<const uint4 *>(job.mb + mbi));
+    const bool up = mb_row != 0, left = mb_col != 0;
+    const bool right = mb_col != g.mb_cols - 1;
+
+    /* ---- wait for the intra neighbours: left, above-left, above, above-right ---- */
+    if (lane < 4) {
+        const int dr = lane == 0 ? 0 : -1, dc = lane == 0 ? -1 : lane - 2;
+        const bool exists = (lane == 0) ? left : (up && (dc < 0 ? left : (dc > 0 ? right : true)));
+        if (exists) {
+            const int ni = mbi + dr * g.mb_cols + dc;
+            if (__ldg(reinterpret_cast<const unsigned *>(job.mb + ni)) >> 16 & 0xff) { /* inter: final since k_inter */ }
+            else while (ld_acquire(job.done + ni) != epoch) __nanosleep(100);
+        }
+    }
+    __syncwarp();
+
+    uint8_t *YT = s_yt[warp] + YS + 16;                  /* tile pixel (0,0) */
+    uint8_t *UT = s_ct[warp][0] + CS + 4, *VT = s_ct[warp][1] + CS + 4;
+    uint8_t *const dy = job.dst + g.y_off + (size_t)mb_row * 16 * g.y_stride + mb_col * 16;
+    uint8_t *const du = job.dst + g.u_off + (size_t)mb_row * 8 * g.uv_stride + mb_col * 8;
+    uint8_t *const dv = job.dst + g.v_off + (size_t)mb_row * 8 * g.uv_stride + mb_col * 8;
+
+    /* ---- borders into the tiles (setupintrarecon.c:15-32 rules at frame edges) ---- */
+    int a_px = 127, l_px = 129;                           /* this lane's above / left border pixel */
+    {
+        if (lane < 21) {                                  /* luma above row, cols -1..19 */
+            const int c = lane - 1;
+            int v;
+            if (!up) v = 127;
+            else if (c < 0) v = left ? __ldcg(dy - g.y_stride - 1) : 129;
+            else if (c >= 16 && !right) v = __ldcg(dy - g.y_stride + 15);       /* extend.c:160-185 */
+            else v = __ldcg(dy - g.y_stride + c);
+            YT[-YS + c] = (uint8_t)v;
+        }
+        if (lane < 16) {                                  /* luma left column */
+            const int v = left ? __ldcg(dy + lane * g.y_stride - 1) : 129;
+            YT[lane * YS - 1] = (uint8_t)v;
+        }
+        const int half = lane >> 4, q = lane & 15;        /* chroma: U on lanes 0-15, V on 16-31 */
+        uint8_t *CT = half ? VT : UT;
+        const uint8_t *pl = half ? dv : du;
+        if (q < 9) {
+            const int c = q - 1;
+            int v;
+            if (!up) v = 127;
+            else if (c < 0) v = left ? __ldcg(pl - g.uv_stride - 1) : 129;
+            else v = __ldcg(pl - g.uv_stride + c);
+            CT[-CS + c] = (uint8_t)v;
+        }
+        if (q < 8) {
+            const int v = left ? __ldcg(pl + q * g.uv_stride - 1) : 129;
+            CT[q * CS - 1] = (uint8_t)v;
+        }
+    }
+    __syncwarp();
+    /* ---- DC values (reconintra.c:167-195, :434-462): lanes 0-15 sum luma, 16-23 U, 24-31 V ---- */
+    int dc;
+    {
+        const uint8_t *T = lane < 16 ? YT : (lane < 24 ? UT : VT);
+        const int ts = lane < 16 ? YS : CS, i = lane < 16 ? lane : (lane & 7);
+        a_px = up ? T[-ts + i] : 0;
+        l_px = left ? T[i * ts - 1] : 0;
+        int s = a_px + l_px;
+        /* segmented sums: 16 lanes, 8 lanes, 8 lanes */
+        s += __shfl_xor_sync(FULL_MASK, s, 1);
+        s += __shfl_xor_sync(FULL_MASK, s, 2);
+        s += __shfl_xor_sync(FULL_MASK, s, 4);
+        const int s8 = s;
+        s += __shfl_xor_sync(FULL_MASK, s, 8);
+        const int sum = lane < 16 ? s : s8;
+        const int lg = lane < 16 ? 3 : 2;
+        const int shift = lg + (up ? 1 : 0) + (left ? 1 : 0);
+        dc = (up || left) ? (sum + (1 << (shift - 1))) >> shift : 128;
+    }
+    const int dc_y = __shfl_sync(FULL_MASK, dc, 0), dc_u = __shfl_sync(FULL_MASK, dc, 16), dc_v = __shfl_sync(FULL_MASK, dc, 24);
+
+    /* ---- chroma (lanes 16..23) and whole-block luma (lanes 0..15), lane = 4x4 block ---- */
+    const bool bpred = mb.y_mode == VP8B200_B_PRED;
+    if (lane >= 16 && lane < 24) {
+        const int j = lane & 3, bx = (j & 1) * 4, by = (j >> 1) * 4;
+        unsigned px[4];
+        block_mode(mb.uv_mode, lane < 20 ? UT : VT, CS, bx, by, lane < 20 ? dc_u : dc_v, px);
+        add_residual(job, mb, lane, false, px);
+        store4x4((lane < 20 ? du : dv) + by * g.uv_stride + bx, g.uv_stride, px);
+    } else if (lane < 16) {
+        const int bx = (lane & 3) * 4, by = (lane >> 2) * 4;
+        if (!bpred) {
+            unsigned px[4];
+            block_mode(mb.y_mode, YT, YS, bx, by, dc_y, px);
+            add_residual(job, mb, lane, true, px);
+            store4x4(dy + by * g.y_stride + bx, g.y_stride, px);
+        } else {
+            /* residuals of the 16 sub-blocks first: they do not depend on prediction */
+            int res[16];
+            bpred_residual(job, mb, lane, res);
+            uint4 *o = reinterpret_cast<uint4 *>(s_res[warp][lane]);
+            o[0] = make_uint4((res[0] & 0xffff) | (res[1] << 16), (res[2] & 0xffff) | (res[3] << 16),
+                              (res[4] & 0xffff) | (res[5] << 16), (res[6] & 0xffff) | (res[7] << 16));
+            o[1] = make_uint4((res[8] & 0xffff) | (res[9] << 16), (res[10] & 0xffff) | (res[11] << 16),
+                              (res[12] & 0xffff) | (res[13] << 16), (res[14] & 0xffff) | (res[15] << 16));
+        }
+    }
+    if (bpred) {
+        /* 16 sub-blocks, anti-diagonal wavefront: block (br,bc) at step bc + 2*br needs left,
+         * above and above-right (decodframe.c:200-237).  Two blocks per step at most: lanes
+         * 0-15 are the pixels of the first, 16-31 of the second. */
+        const uint8_t *modes = reinterpret_cast<const uint8_t *>(job.aux + mb.u.aux);
+        const int pix = lane & 15, pr = pix >> 2, pc = pix & 3, which = lane >> 4;
+        __syncwarp();
+#pragma unroll 1
+        for (int step = 0; step < 10; step++) {
+            /* blocks on this anti-diagonal: br from max(0,(step-3+1)/2) .. min(3, step/2) */
+            const int br_lo = step > 3 ? (step - 2) >> 1 : 0;
+            const int br = br_lo + which, bc = step - 2 * br;
+            const bool act = br <= 3 && bc >= 0 && bc <= 3 && br <= (step >> 1);
+            if (act) {
+                const int blk = br * 4 + bc;
+                const int mode = modes[blk];
+                uint8_t *B = YT + br * 4 * YS + bc * 4;              /* block pixel (0,0) */
+                /* edge array element e: 0..3 = L3..L0, 4 = top-left, 5..12 = above / above-right;
+                 * column 3 takes its above-right from row -1 of the MB (reconintra4x4.c:305-317) */
+                auto E = [&](int e) -> int {
+                    if (e < 4) return B[(3 - e) * YS - 1];
+                    if (e < 9) return B[-YS + e - 5];
+                    return bc == 3 ? YT[-YS + 16 + e - 9] : B[-YS + e - 5];
+                };
+                const unsigned ent = c_bpred[mode][pix];
+                const int kind = ent >> 12;
+                int v;
+                if (kind == 0) v = (E(ent & 15) + 2 * E((ent >> 4) & 15) + E((ent >> 8) & 15) + 2) >> 2;
+                else if (kind == 1) v = (E(ent & 15) + E((ent >> 4) & 15) + 1) >> 1;
+                else if (kind == 2) v = (E(5) + E(6) + E(7) + E(8) + E(0) + E(1) + E(2) + E(3) + 4) >> 3;
+                else v = clamp255(E(5 + pc) - E(4) + E(3 - pr));
+                v = clamp255(v + s_res[warp][blk][pix]);
+                B[pr * YS + pc] = (uint8_t)v;
+            }
+            __syncwarp();
+        }
+        /* the finished 16x16 goes out row by row */
+        if (lane < 16) {
+            const unsigned *r = reinterpret_cast<const unsigned *>(YT + lane * YS);
+            *reinterpret_cast<uint4 *>(dy + lane * g.y_stride) = make_uint4(r[0], r[1], r[2], r[3]);
+        }
+    }
+    /* ---- publish: this macroblock's unfiltered reconstruction is final ---- */
+    __syncwarp();
+    if (lane == 0) st_release(job.done + mbi, epoch);
+}
+
+void vp8b200_launch_intra(cudaStream_t s, const FrameJob *jobs, int n_jobs, const Geo &g,
+                          unsigned int max_intra, unsigned int *ticket, unsigned int ticket_base,
+                          int *n_ctas)
+{
+    const unsigned long long warps = (unsigned long long)max_intra * (unsigned)n_jobs;
+    const int ctas = (int)((warps + INTRA_WARPS - 1) / INTRA_WARPS);
+    *n_ctas = ctas;
+    if (ctas) k_intra<<<ctas, INTRA_WARPS * 32, 0, s>>>(jobs, n_jobs, g, max_intra, ticket, ticket_base);
+}

@@ -29,6 +29,7 @@ struct Slot {
     vp8b200_aux *h_aux, *d_aux;
     int16_t *h_coef, *d_coef;
     FrameJob *h_job, *d_job;
+    uint32_t *h_ilist, *d_ilist;   /* intra MB indices in wavefront order (P frames) */
     cudaEvent_t h2d_done;
     bool pending;
 };
@@ -39,6 +40,7 @@ struct vp8b200_staged {
     vp8b200_mb *d_mb;
     vp8b200_aux *d_aux;
     int16_t *d_coef;
+    uint32_t *d_ilist;             /* NULL on key frames: the context's static order is used */
     unsigned n_intra;
 };
 
@@ -54,7 +56,9 @@ struct vp8b200_ctx {
     int cur;
     bool open;
     vp8b200_frame_hdr cur_hdr;
-    unsigned *d_progress;          /* 2*mb_rows wavefront counters */
+    unsigned *d_done;              /* per-MB intra "done" flags (epoch values) */
+    uint32_t *d_diag;              /* all MB indices sorted by wavefront index c + 2r */
+    int *diag_tmp;                 /* host scratch for the counting sort */
     uint8_t *d_lfmsg;              /* loop-filter row hand-off messages, 256 B per MB */
     unsigned *d_tickets;           /* [0] intra, [1] loop filter */
     unsigned ticket_base[2];
@@ -123,6 +127,7 @@ static void free_ctx(vp8b200_ctx *c)
     for (int i = 0; i < NSLOT; i++) {
         Slot &s = c->slot[i];
         cudaFreeHost(s.h_mb); cudaFreeHost(s.h_aux); cudaFreeHost(s.h_coef); cudaFreeHost(s.h_job);
+        cudaFreeHost(s.h_ilist); cudaFree(s.d_ilist);
         cudaFree(s.d_mb); cudaFree(s.d_aux); cudaFree(s.d_coef); cudaFree(s.d_job);
         if (s.h2d_done) cudaEventDestroy(s.h2d_done);
     }
@@ -130,7 +135,8 @@ static void free_ctx(vp8b200_ctx *c)
         cudaFreeHost(c->h_bjobs[i]); cudaFree(c->d_bjobs[i]);
         if (c->bjobs_done[i]) cudaEventDestroy(c->bjobs_done[i]);
     }
-    cudaFree(c->d_progress); cudaFree(c->d_tickets); cudaFree(c->d_lfmsg);
+    cudaFree(c->d_done); cudaFree(c->d_diag); cudaFree(c->d_tickets); cudaFree(c->d_lfmsg);
+    free(c->diag_tmp);
     if (c->fetch_done) cudaEventDestroy(c->fetch_done);
     if (c->spans) {
         for (auto &sp : *c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -141,12 +147,35 @@ static void free_ctx(vp8b200_ctx *c)
     delete c;
 }
 
+/* Indices of the intra macroblocks (all macroblocks when mb == NULL) sorted by wavefront
+ * index d = col + 2*row, raster order inside one d (counting sort).  Every neighbour an intra
+ * MB depends on (left d-1, above-left d-3, above d-2, above-right d-1) sorts before it. */
+static unsigned wavefront_order(const Geo &g, const vp8b200_mb *mb, uint32_t n_mb, uint32_t *out, int *cnt)
+{
+    const int nd = g.mb_cols + 2 * g.mb_rows;
+    for (int d = 0; d <= nd; d++) cnt[d] = 0;
+    for (uint32_t i = 0; i < n_mb; i++)
+        if (!mb || mb[i].ref_frame == VP8B200_INTRA_FRAME) {
+            const int r = (int)(i / (uint32_t)g.mb_cols), c = (int)(i % (uint32_t)g.mb_cols);
+            cnt[c + 2 * r + 1]++;
+        }
+    for (int d = 0; d < nd; d++) cnt[d + 1] += cnt[d];
+    const unsigned total = (unsigned)cnt[nd];
+    for (uint32_t i = 0; i < n_mb; i++)
+        if (!mb || mb[i].ref_frame == VP8B200_INTRA_FRAME) {
+            const int r = (int)(i / (uint32_t)g.mb_cols), c = (int)(i % (uint32_t)g.mb_cols);
+            out[cnt[c + 2 * r]++] = i;
+        }
+    return total;
+}
+
 static int create_impl(vp8b200_ctx *c)
 {
     const Geo &g = c->geo;
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     vp8b200_upload_constants();
+    vp8b200_upload_intra_constants();
     CK(c, cudaGetLastError());
     for (int i = 0; i < c->n_fb; i++) {
         CK(c, cudaMalloc((void **)&c->fb[i], c->frame_size));
@@ -163,11 +192,25 @@ static int create_impl(vp8b200_ctx *c)
         CK(c, cudaMalloc((void **)&s.d_aux, n_mb * sizeof(vp8b200_aux)));
         CK(c, cudaMalloc((void **)&s.d_coef, n_mb * 25 * 32));
         CK(c, cudaMalloc((void **)&s.d_job, sizeof(FrameJob)));
+        CK(c, cudaHostAlloc((void **)&s.h_ilist, n_mb * sizeof(uint32_t), cudaHostAllocPortable));
+        CK(c, cudaMalloc((void **)&s.d_ilist, n_mb * sizeof(uint32_t)));
         CK(c, cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
     }
     for (int i = 0; i < NBJOB; i++) CK(c, cudaEventCreateWithFlags(&c->bjobs_done[i], cudaEventDisableTiming));
-    CK(c, cudaMalloc((void **)&c->d_progress, 2 * g.mb_rows * sizeof(unsigned)));
-    CK(c, cudaMemsetAsync(c->d_progress, 0, 2 * g.mb_rows * sizeof(unsigned), c->stream));
+    CK(c, cudaMalloc((void **)&c->d_done, n_mb * sizeof(unsigned)));
+    CK(c, cudaMemsetAsync(c->d_done, 0, n_mb * sizeof(unsigned), c->stream));
+    CK(c, cudaMalloc((void **)&c->d_diag, n_mb * sizeof(uint32_t)));
+    c->diag_tmp = (int *)malloc(sizeof(int) * (size_t)(g.mb_cols + 2 * g.mb_rows + 2));
+    if (!c->diag_tmp) return VP8B200_ERR_NOMEM;
+    {
+        /* static wavefront order of ALL macroblocks (key frames) */
+        uint32_t *tmp = (uint32_t *)malloc(n_mb * sizeof(uint32_t));
+        if (!tmp) return VP8B200_ERR_NOMEM;
+        wavefront_order(g, NULL, (uint32_t)n_mb, tmp, c->diag_tmp);
+        cudaError_t e = cudaMemcpy(c->d_diag, tmp, n_mb * sizeof(uint32_t), cudaMemcpyHostToDevice);
+        free(tmp);
+        CK(c, e);
+    }
     CK(c, cudaMalloc((void **)&c->d_lfmsg, (size_t)c->n_mb * 256));
     CK(c, cudaMemsetAsync(c->d_lfmsg, 0, (size_t)c->n_mb * 256, c->stream));
     CK(c, cudaMalloc((void **)&c->d_tickets, 2 * sizeof(unsigned)));
@@ -256,13 +299,6 @@ extern "C" int vp8b200_frame_abort(vp8b200_ctx *c)
     return VP8B200_OK;
 }
 
-static unsigned count_intra(const vp8b200_mb *mb, uint32_t n)
-{
-    unsigned k = 0;
-    for (uint32_t i = 0; i < n; i++) k += mb[i].ref_frame == VP8B200_INTRA_FRAME;
-    return k;
-}
-
 /* validate what the kernels will index with (a corrupt record must not become a wild read) */
 static bool records_ok(const Geo &g, const vp8b200_mb *mb, const vp8b200_aux *aux, uint32_t n_mb,
                        uint32_t n_aux, uint32_t n_coef, bool key)
@@ -295,14 +331,15 @@ static bool records_ok(const Geo &g, const vp8b200_mb *mb, const vp8b200_aux *au
 }
 
 static void fill_job(vp8b200_ctx *c, FrameJob *j, const vp8b200_frame_hdr &h, const vp8b200_mb *d_mb,
-                     const vp8b200_aux *d_aux, const int16_t *d_coef, unsigned n_intra,
-                     bool run_intra, bool run_lf)
+                     const vp8b200_aux *d_aux, const int16_t *d_coef, const uint32_t *d_ilist,
+                     unsigned n_intra, bool run_intra, bool run_lf)
 {
     memset(j, 0, sizeof *j);
     j->dst = c->fb[h.fb_new];
     j->ref[1] = c->fb[h.fb_last]; j->ref[2] = c->fb[h.fb_golden]; j->ref[3] = c->fb[h.fb_altref];
     j->mb = d_mb; j->aux = d_aux; j->coef = d_coef;
-    j->progress = c->d_progress;
+    j->done = c->d_done;
+    j->intra_list = d_ilist ? d_ilist : c->d_diag;
     j->lf_msg = c->d_lfmsg;
     if (run_intra) c->epoch_intra++;
     if (run_lf) c->epoch_lf++;
@@ -326,8 +363,9 @@ static void prof_mark(vp8b200_ctx *c, int kind, bool begin)
     }
 }
 
-static int run_jobs(vp8b200_ctx *c, const FrameJob *d_jobs, int n, bool any_inter, bool any_intra, bool any_lf)
+static int run_jobs(vp8b200_ctx *c, const FrameJob *d_jobs, int n, bool any_inter, unsigned max_intra, bool any_lf)
 {
+    const bool any_intra = max_intra > 0;
     int nctas = 0;
     unsigned k = 0;
     if (any_inter) {
@@ -337,7 +375,7 @@ static int run_jobs(vp8b200_ctx *c, const FrameJob *d_jobs, int n, bool any_inte
     }
     if (any_intra) {
         prof_mark(c, 1, true);
-        vp8b200_launch_intra(c->stream, d_jobs, n, c->geo, c->d_tickets + 0, c->ticket_base[0], &nctas);
+        vp8b200_launch_intra(c->stream, d_jobs, n, c->geo, max_intra, c->d_tickets + 0, c->ticket_base[0], &nctas);
         prof_mark(c, 1, false);
         c->ticket_base[0] += (unsigned)nctas; k++;
     }
@@ -370,9 +408,12 @@ extern "C" int vp8b200_frame_submit(vp8b200_ctx *c, uint32_t n_aux, uint32_t n_c
         snprintf(c->err, sizeof c->err, "macroblock records failed validation");
         return VP8B200_ERR_INVALID;
     }
-    const unsigned n_intra = count_intra(s.h_mb, c->n_mb);
+    /* key frames use the context's static wavefront order; P frames list their intra MBs */
+    const unsigned n_intra = key ? c->n_mb : wavefront_order(c->geo, s.h_mb, c->n_mb, s.h_ilist, c->diag_tmp);
     const bool run_intra = n_intra > 0, run_lf = h.filter_level != 0;
-    fill_job(c, s.h_job, h, s.d_mb, s.d_aux, s.d_coef, n_intra, run_intra, run_lf);
+    fill_job(c, s.h_job, h, s.d_mb, s.d_aux, s.d_coef, key ? NULL : s.d_ilist, n_intra, run_intra, run_lf);
+    if (!key && n_intra)
+        CK(c, cudaMemcpyAsync(s.d_ilist, s.h_ilist, (size_t)n_intra * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     CK(c, cudaMemcpyAsync(s.d_mb, s.h_mb, (size_t)c->n_mb * sizeof(vp8b200_mb), cudaMemcpyHostToDevice, c->stream));
     if (n_aux) CK(c, cudaMemcpyAsync(s.d_aux, s.h_aux, (size_t)n_aux * sizeof(vp8b200_aux), cudaMemcpyHostToDevice, c->stream));
     if (n_coef) CK(c, cudaMemcpyAsync(s.d_coef, s.h_coef, (size_t)n_coef * 32, cudaMemcpyHostToDevice, c->stream));
@@ -380,8 +421,8 @@ extern "C" int vp8b200_frame_submit(vp8b200_ctx *c, uint32_t n_aux, uint32_t n_c
     CK(c, cudaEventRecord(s.h2d_done, c->stream));
     s.pending = true;
     g_h2d_bytes += (uint64_t)c->n_mb * sizeof(vp8b200_mb) + (uint64_t)n_aux * sizeof(vp8b200_aux) +
-                   (uint64_t)n_coef * 32 + sizeof(FrameJob);
-    int st = run_jobs(c, s.d_job, 1, !key, run_intra, run_lf);
+                   (uint64_t)n_coef * 32 + sizeof(FrameJob) + (key ? 0 : (uint64_t)n_intra * 4);
+    int st = run_jobs(c, s.d_job, 1, !key, n_intra, run_lf);
     c->cur = (c->cur + 1) % NSLOT;
     return st;
 }
@@ -447,9 +488,19 @@ extern "C" int vp8b200_stage_frame(vp8b200_ctx *c, const vp8b200_frame_hdr *hdr,
     const size_t aux_b = ((size_t)n_aux * sizeof(vp8b200_aux) + 255) & ~(size_t)255;
     const size_t coef_b = (size_t)n_coef * 32;
     const size_t mb_pad = (mb_b + 255) & ~(size_t)255;
-    cudaError_t e = cudaMalloc((void **)&s->d_blob, mb_pad + aux_b + coef_b + 256);
+    const bool key = hdr->frame_type == 0;
+    uint32_t *ilist = NULL;
+    unsigned n_intra = c->n_mb;
+    if (!key) {
+        ilist = (uint32_t *)malloc((size_t)c->n_mb * sizeof(uint32_t));
+        if (!ilist) { delete s; return VP8B200_ERR_NOMEM; }
+        n_intra = wavefront_order(c->geo, mb, c->n_mb, ilist, c->diag_tmp);
+    }
+    const size_t coef_pad = (coef_b + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc((void **)&s->d_blob, mb_pad + aux_b + coef_pad + (size_t)n_intra * 4 + 256);
     if (e != cudaSuccess) {
         snprintf(c->err, sizeof c->err, "cudaMalloc(staged): %s", cudaGetErrorString(e));
+        free(ilist);
         delete s;
         return VP8B200_ERR_CUDA;
     }
@@ -457,7 +508,15 @@ extern "C" int vp8b200_stage_frame(vp8b200_ctx *c, const vp8b200_frame_hdr *hdr,
     s->d_mb = (vp8b200_mb *)s->d_blob;
     s->d_aux = (vp8b200_aux *)(s->d_blob + mb_pad);
     s->d_coef = (int16_t *)(s->d_blob + mb_pad + aux_b);
-    s->n_intra = count_intra(mb, c->n_mb);
+    s->n_intra = n_intra;
+    s->d_ilist = key ? NULL : (uint32_t *)(s->d_blob + mb_pad + aux_b + coef_pad);
+    if (!key && n_intra) {
+        cudaError_t e2 = cudaMemcpy(s->d_ilist, ilist, (size_t)n_intra * 4, cudaMemcpyHostToDevice);
+        free(ilist);
+        CK(c, e2);
+    } else {
+        free(ilist);
+    }
     /* staging is a setup-time operation: plain synchronous copies from pageable memory */
     CK(c, cudaMemcpy(s->d_mb, mb, mb_b, cudaMemcpyHostToDevice));
     if (n_aux) CK(c, cudaMemcpy(s->d_aux, aux, (size_t)n_aux * sizeof(vp8b200_aux), cudaMemcpyHostToDevice));
@@ -497,25 +556,26 @@ extern "C" int vp8b200_batch_run(vp8b200_ctx *const *ctx, vp8b200_staged *const 
     }
     const int r = c->bjobs_cur;
     if (c->bjobs_pending[r]) { CK(c, cudaEventSynchronize(c->bjobs_done[r])); c->bjobs_pending[r] = false; }
-    bool any_inter = false, any_intra = false, any_lf = false;
+    bool any_inter = false, any_lf = false;
+    unsigned max_intra = 0;
     for (int i = 0; i < n; i++) {
         const vp8b200_staged *s = frame[i];
-        const bool run_intra = s->n_intra > 0, run_lf = s->hdr.filter_level != 0;
-        any_inter |= s->hdr.frame_type != 0; any_intra |= run_intra; any_lf |= run_lf;
+        any_inter |= s->hdr.frame_type != 0; any_lf |= s->hdr.filter_level != 0;
+        if (s->n_intra > max_intra) max_intra = s->n_intra;
     }
     for (int i = 0; i < n; i++) {
         const vp8b200_staged *s = frame[i];
-        /* every job of a launched wavefront kernel publishes progress, so every context's
-         * epoch advances with the launch, not with its own need for the kernel */
-        fill_job(ctx[i], &c->h_bjobs[r][i], s->hdr, s->d_mb, s->d_aux, s->d_coef, s->n_intra,
-                 any_intra, any_lf && s->hdr.filter_level != 0);
+        /* a context's intra / loop-filter epoch advances only when that kernel really has
+         * work for it (done flags and message tags of idle jobs stay untouched) */
+        fill_job(ctx[i], &c->h_bjobs[r][i], s->hdr, s->d_mb, s->d_aux, s->d_coef, s->d_ilist, s->n_intra,
+                 s->n_intra > 0, any_lf && s->hdr.filter_level != 0);
     }
     CK(c, cudaMemcpyAsync(c->d_bjobs[r], c->h_bjobs[r], (size_t)n * sizeof(FrameJob), cudaMemcpyHostToDevice, c->stream));
     g_h2d_bytes += (uint64_t)n * sizeof(FrameJob);
     CK(c, cudaEventRecord(c->bjobs_done[r], c->stream));
     c->bjobs_pending[r] = true;
     c->bjobs_cur = (r + 1) % NBJOB;
-    return run_jobs(c, c->d_bjobs[r], n, any_inter, any_intra, any_lf);
+    return run_jobs(c, c->d_bjobs[r], n, any_inter, max_intra, any_lf);
 }
 
 /* ---- statistics and per-kernel profiling -------------------------------------------------- */

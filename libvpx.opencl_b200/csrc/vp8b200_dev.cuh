@@ -163,4 +163,76 @@ __device__ __forceinline__ void add_residual(const FrameJob &job, const vp8b200_
     }
 }
 
+/* 4x4 inverse DCT only (idctllm.c:28-92): 16 residual values, before the add */
+__device__ __forceinline__ void idct4x4(const int (&in)[16], int (&out)[16])
+{
+    int mid[16];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int a = in[i] + in[8 + i];
+        int b = in[i] - in[8 + i];
+        int t1 = (in[4 + i] * 35468) >> 16;
+        int t2 = in[12 + i] + ((in[12 + i] * 20091) >> 16);
+        int c = t1 - t2;
+        t1 = in[4 + i] + ((in[4 + i] * 20091) >> 16);
+        t2 = (in[12 + i] * 35468) >> 16;
+        int d = t1 + t2;
+        mid[i]      = s16(a + d);
+        mid[12 + i] = s16(a - d);
+        mid[4 + i]  = s16(b + c);
+        mid[8 + i]  = s16(b - c);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        int m0 = mid[4 * r], m1 = mid[4 * r + 1], m2 = mid[4 * r + 2], m3 = mid[4 * r + 3];
+        int a = m0 + m2;
+        int b = m0 - m2;
+        int t1 = (m1 * 35468) >> 16;
+        int t2 = m3 + ((m3 * 20091) >> 16);
+        int c = t1 - t2;
+        t1 = m1 + ((m1 * 20091) >> 16);
+        t2 = (m3 * 35468) >> 16;
+        int d = t1 + t2;
+        out[4 * r + 0] = s16((a + d + 4) >> 3);
+        out[4 * r + 3] = s16((a - d + 4) >> 3);
+        out[4 * r + 1] = s16((b + c + 4) >> 3);
+        out[4 * r + 2] = s16((b - c + 4) >> 3);
+    }
+}
+
+/* Residual of a B_PRED luma sub-block (no Y2): 16 values, all zero when the block carries
+ * no coefficients (decodframe.c:217-236). */
+__device__ __forceinline__ void bpred_residual(const FrameJob &job, const vp8b200_mb &mb, int blk, int (&res)[16])
+{
+#pragma unroll
+    for (int i = 0; i < 16; i++) res[i] = 0;
+    if (mb.flags & VP8B200_MBF_SKIP) return;
+    const unsigned mask = mb.coef_mask;
+    if (!((mask >> blk) & 1u)) return;
+    const int16_t(*dq)[2] = job.hdr.dequant[mb.flags & VP8B200_MBF_SEGMENT_MASK];
+    int q[16];
+    load_coefs(job.coef + ((size_t)mb.coef_off + __popc(mask & ((1u << blk) - 1u))) * 16, q);
+    q[0] = s16(q[0] * dq[0][0]);
+#pragma unroll
+    for (int i = 1; i < 16; i++) q[i] = s16(q[i] * dq[0][1]);
+    idct4x4(q, res);
+}
+
+__device__ __forceinline__ void store4x4(uint8_t *dst, int stride, const unsigned (&px)[4])
+{
+#pragma unroll
+    for (int r = 0; r < 4; r++) *reinterpret_cast<unsigned *>(dst + r * stride) = px[r];
+}
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 #endif

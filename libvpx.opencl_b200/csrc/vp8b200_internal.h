@@ -23,7 +23,8 @@ struct FrameJob {
     const vp8b200_mb *mb;
     const vp8b200_aux *aux;
     const int16_t *coef;
-    unsigned int *progress;       /* [0,mb_rows): intra wavefront progress counters           */
+    unsigned int *done;           /* per-MB "intra reconstruction finished" flags (= epoch)   */
+    const uint32_t *intra_list;   /* indices of the intra MBs, sorted by wavefront c + 2r     */
     uint8_t *lf_msg;              /* loop-filter row hand-off: 256 B per macroblock           */
     unsigned int epoch_intra;     /* progress values of this frame are (epoch << 13) + columns; */
     unsigned int epoch_lf;        /* each counter advances only when its kernel really runs     */
@@ -33,13 +34,15 @@ struct FrameJob {
 
 #define VP8B200_EPOCH_SHIFT 13    /* mb_cols <= 4096 < 2^13 */
 
-void vp8b200_upload_constants();   /* filter taps -> __constant__ on the current device */
+void vp8b200_upload_constants();        /* filter taps -> __constant__ on the current device */
+void vp8b200_upload_intra_constants();  /* B_PRED predictor table */
 
 /* launch wrappers (kernels_*.cu); `tickets` points at two device counters owned by the
  * launching context, ticket_base = value of the counter before this launch */
 void vp8b200_launch_inter(cudaStream_t s, const FrameJob *jobs, int n_jobs, const Geo &g);
 void vp8b200_launch_intra(cudaStream_t s, const FrameJob *jobs, int n_jobs, const Geo &g,
-                          unsigned int *ticket, unsigned int ticket_base, int *n_ctas);
+                          unsigned int max_intra, unsigned int *ticket, unsigned int ticket_base,
+                          int *n_ctas);
 void vp8b200_launch_loopfilter(cudaStream_t s, const FrameJob *jobs, int n_jobs, const Geo &g,
                                unsigned int *ticket, unsigned int ticket_base, int *n_ctas);
 void vp8b200_launch_border(cudaStream_t s, const FrameJob *jobs, int n_jobs, const Geo &g);
