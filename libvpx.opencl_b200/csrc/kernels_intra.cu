@@ -13,7 +13,8 @@
  * k_inter); warps take list entries through an atomic ticket in that order, so every
  * dependency belongs to an earlier ticket, i.e. to a warp that is already running: no
  * deadlock, and no reliance on block scheduling order.  A warp waits only for those of its
- * four neighbours that are themselves intra (per-MB done flags, release/acquire).
+ * four neighbours that are themselves intra, by polling the tagged border words they export
+ * (no flags, no fences).
  *
  * Inside a macroblock: borders are gathered into a shared-memory tile (frame-edge values are
  * synthesised, never read from the frame), residuals of all blocks are computed first
@@ -130,6 +131,9 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
     __shared__ __align__(16) uint8_t s_yt[INTRA_WARPS][17 * YS];
     __shared__ __align__(16) uint8_t s_ct[INTRA_WARPS][2][9 * CS];
     __shared__ __align__(16) short s_res[INTRA_WARPS][16][16];
+    __shared__ uint8_t s_modes[INTRA_WARPS][16];
+    __shared__ unsigned short s_bpred[160];              /* per-lane indexing: shared, not constant */
+    for (int i = threadIdx.x; i < 160; i += blockDim.x) s_bpred[i] = (&c_bpred[0][0])[i];
     if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u) - ticket_base;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -153,17 +157,21 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
     const bool up = mb_row != 0, left = mb_col != 0;
     const bool right = mb_col != g.mb_cols - 1;
 
-    /* ---- wait for the intra neighbours: left, above-left, above, above-right ---- */
-    if (lane < 4) {
-        const int dr = lane == 0 ? 0 : -1, dc = lane == 0 ? -1 : lane - 2;
-        const bool exists = (lane == 0) ? left : (up && (dc < 0 ? left : (dc > 0 ? right : true)));
-        if (exists) {
-            const int ni = mbi + dr * g.mb_cols + dc;
-            if (__ldg(reinterpret_cast<const unsigned *>(job.mb + ni)) >> 16 & 0xff) { /* inter: final since k_inter */ }
-            else while (ld_acquire(job.done + ni) != epoch) __nanosleep(100);
-        }
+    /* ---- residuals first: they need only the coefficient records, so their global loads and
+     * the IDCT / WHT overlap the wait for the neighbours (lane = 4x4 block) ---- */
+    const bool bpred = mb.y_mode == VP8B200_B_PRED;
+    int res[16];
+    bool has_res = false;
+    if (lane < 24) has_res = block_residual(job, mb, lane, !bpred, res);
+    if (bpred && lane < 16) {
+        uint4 *o = reinterpret_cast<uint4 *>(s_res[warp][lane]);
+        o[0] = make_uint4((res[0] & 0xffff) | (res[1] << 16), (res[2] & 0xffff) | (res[3] << 16),
+                          (res[4] & 0xffff) | (res[5] << 16), (res[6] & 0xffff) | (res[7] << 16));
+        o[1] = make_uint4((res[8] & 0xffff) | (res[9] << 16), (res[10] & 0xffff) | (res[11] << 16),
+                          (res[12] & 0xffff) | (res[13] << 16), (res[14] & 0xffff) | (res[15] << 16));
     }
-    __syncwarp();
+    if (bpred && lane < 16) s_modes[warp][lane] = reinterpret_cast<const uint8_t *>(job.aux + mb.u.aux)[lane];
+    const int pix = lane & 15, pr = pix >> 2, pc = pix & 3, which = lane >> 4;
 
     uint8_t *YT = s_yt[warp] + YS + 16;                  /* tile pixel (0,0) */
     uint8_t *UT = s_ct[warp][0] + CS + 4, *VT = s_ct[warp][1] + CS + 4;
@@ -171,39 +179,84 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
     uint8_t *const du = job.dst + g.u_off + (size_t)mb_row * 8 * g.uv_stride + mb_col * 8;
     uint8_t *const dv = job.dst + g.v_off + (size_t)mb_row * 8 * g.uv_stride + mb_col * 8;
 
-    /* ---- borders into the tiles (setupintrarecon.c:15-32 rules at frame edges) ---- */
-    int a_px = 127, l_px = 129;                           /* this lane's above / left border pixel */
+    /* ---- borders.  Every finished intra MB exports its bottom row and right column as 16
+     * tagged 64-bit words (W0-3 Y row 15, W4-5 U row 7, W6-7 V row 7, W8-11 Y column 15,
+     * W12-13 U column 7, W14-15 V column 7; {32 bits of pixels, 32-bit frame tag}).  A word
+     * whose tag matches is valid (aligned 64-bit accesses are single-copy atomic), so the
+     * consumer polls the words themselves: no flag, no fence, no second round trip, and the
+     * producer's frame stores are off the dependency chain.  Inter neighbours were finished by
+     * k_inter and are read from the frame; frame edges are synthesised (setupintrarecon.c:15-32,
+     * extend.c:160-185).  Lanes 0-7 left column words, 8-15 above row words, 16-18 the top-left
+     * pixels of Y/U/V, 19 the above-right luma word. ---- */
     {
-        if (lane < 21) {                                  /* luma above row, cols -1..19 */
-            const int c = lane - 1;
-            int v;
-            if (!up) v = 127;
-            else if (c < 0) v = left ? __ldcg(dy - g.y_stride - 1) : 129;
-            else if (c >= 16 && !right) v = __ldcg(dy - g.y_stride + 15);       /* extend.c:160-185 */
-            else v = __ldcg(dy - g.y_stride + c);
-            YT[-YS + c] = (uint8_t)v;
+        const unsigned long long *msg = job.intra_msg;
+        unsigned w = 0;
+        if (lane < 20) {
+            /* which neighbour this lane reads, which word of its export, or which frame bytes */
+            const int grp = lane < 8 ? 0 : (lane < 16 ? 1 : (lane < 19 ? 2 : 3));   /* left, above, above-left, above-right */
+            const bool exists = grp == 0 ? left : (up && (grp == 2 ? left : (grp == 3 ? right : true)));
+            const int ni = mbi + (grp == 0 ? -1 : (grp == 1 ? -g.mb_cols : (grp == 2 ? -g.mb_cols - 1 : -g.mb_cols + 1)));
+            const int j = grp == 0 ? lane : (grp == 1 ? lane - 8 : lane - 16);     /* index inside the group */
+            /* plane of the word: words 0-3 Y, 4-5 U, 6-7 V (both for rows and columns) */
+            const int pl = grp >= 2 ? (grp == 3 ? 0 : j) : (j < 4 ? 0 : (j < 6 ? 1 : 2));
+            const int stride = pl == 0 ? g.y_stride : g.uv_stride;
+            const uint8_t *base = pl == 0 ? dy : (pl == 1 ? du : dv);
+            const int size = pl == 0 ? 16 : 8;
+            if (!exists) {
+                /* row above the frame is 127 (incl. top-left and above-right), column left of it 129;
+                 * above-right of the last column replicates the above MB's last pixel (filled below) */
+                w = (grp == 0 || (grp == 2 && up)) ? 0x81818181u : 0x7f7f7f7fu;
+            } else {
+                const bool n_intra = ((__ldg(reinterpret_cast<const unsigned *>(job.mb + ni)) >> 16) & 0xff) == VP8B200_INTRA_FRAME;
+                if (n_intra) {
+                    const int word = grp == 0 ? 8 + j : (grp == 1 ? j : (grp == 2 ? 3 + 2 * j : 0));
+                    const unsigned long long *p = msg + (size_t)ni * 16 + word;
+                    unsigned long long v;
+                    for (;;) {
+                        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+                        if ((unsigned)(v >> 32) == epoch) break;
+                        __nanosleep(32);
+                    }
+                    w = (unsigned)v;
+                } else if (grp == 0) {
+                    /* 4 pixels of the column left of the MB: rows 4*jj .. 4*jj+3 of plane pl */
+                    const int jj = pl == 0 ? j : (j & 1);
+                    const uint8_t *q = base + (size_t)(4 * jj) * stride - 1;
+                    w = q[0] | (q[stride] << 8) | (q[2 * stride] << 16) | ((unsigned)q[3 * stride] << 24);
+                } else if (grp == 1) {
+                    const int jj = pl == 0 ? j : (j & 1);
+                    w = *reinterpret_cast<const unsigned *>(base - stride + 4 * jj);
+                } else if (grp == 2) {
+                    w = (unsigned)base[-stride - 1] << 24;                        /* same byte position as in the word */
+                } else {
+                    w = *reinterpret_cast<const unsigned *>(base - stride + size);
+                }
+            }
         }
-        if (lane < 16) {                                  /* luma left column */
-            const int v = left ? __ldcg(dy + lane * g.y_stride - 1) : 129;
-            YT[lane * YS - 1] = (uint8_t)v;
-        }
-        const int half = lane >> 4, q = lane & 15;        /* chroma: U on lanes 0-15, V on 16-31 */
-        uint8_t *CT = half ? VT : UT;
-        const uint8_t *pl = half ? dv : du;
-        if (q < 9) {
-            const int c = q - 1;
-            int v;
-            if (!up) v = 127;
-            else if (c < 0) v = left ? __ldcg(pl - g.uv_stride - 1) : 129;
-            else v = __ldcg(pl - g.uv_stride + c);
-            CT[-CS + c] = (uint8_t)v;
-        }
-        if (q < 8) {
-            const int v = left ? __ldcg(pl + q * g.uv_stride - 1) : 129;
-            CT[q * CS - 1] = (uint8_t)v;
+        /* above-right of the last MB column: replicate the last pixel of the above row */
+        const unsigned w11 = __shfl_sync(FULL_MASK, w, 11);
+        if (lane == 19 && up && !right) w = (w11 >> 24) * 0x01010101u;
+        /* scatter into the tiles */
+        if (lane < 4) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) YT[(4 * lane + i) * YS - 1] = (uint8_t)(w >> (8 * i));
+        } else if (lane < 8) {
+            uint8_t *CT = lane < 6 ? UT : VT;
+#pragma unroll
+            for (int i = 0; i < 4; i++) CT[(4 * (lane & 1) + i) * CS - 1] = (uint8_t)(w >> (8 * i));
+        } else if (lane < 12) {
+            *reinterpret_cast<unsigned *>(YT - YS + 4 * (lane - 8)) = w;
+        } else if (lane < 16) {
+            *reinterpret_cast<unsigned *>((lane < 14 ? UT : VT) - CS + 4 * (lane & 1)) = w;
+        } else if (lane < 19) {
+            uint8_t *T = lane == 16 ? YT : (lane == 17 ? UT : VT);
+            T[-(lane == 16 ? YS : CS) - 1] = (uint8_t)(w >> 24);
+        } else if (lane == 19) {
+            *reinterpret_cast<unsigned *>(YT - YS + 16) = w;
         }
     }
     __syncwarp();
+    int a_px, l_px;
     /* ---- DC values (reconintra.c:167-195, :434-462): lanes 0-15 sum luma, 16-23 U, 24-31 V ---- */
     int dc;
     {
@@ -226,37 +279,25 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
     const int dc_y = __shfl_sync(FULL_MASK, dc, 0), dc_u = __shfl_sync(FULL_MASK, dc, 16), dc_v = __shfl_sync(FULL_MASK, dc, 24);
 
     /* ---- chroma (lanes 16..23) and whole-block luma (lanes 0..15), lane = 4x4 block ---- */
-    const bool bpred = mb.y_mode == VP8B200_B_PRED;
     if (lane >= 16 && lane < 24) {
         const int j = lane & 3, bx = (j & 1) * 4, by = (j >> 1) * 4;
         unsigned px[4];
         block_mode(mb.uv_mode, lane < 20 ? UT : VT, CS, bx, by, lane < 20 ? dc_u : dc_v, px);
-        add_residual(job, mb, lane, false, px);
+        if (has_res) add_res(px, res);
         store4x4((lane < 20 ? du : dv) + by * g.uv_stride + bx, g.uv_stride, px);
-    } else if (lane < 16) {
+        store4x4((lane < 20 ? UT : VT) + by * CS + bx, CS, px);       /* for the export below */
+    } else if (lane < 16 && !bpred) {
         const int bx = (lane & 3) * 4, by = (lane >> 2) * 4;
-        if (!bpred) {
-            unsigned px[4];
-            block_mode(mb.y_mode, YT, YS, bx, by, dc_y, px);
-            add_residual(job, mb, lane, true, px);
-            store4x4(dy + by * g.y_stride + bx, g.y_stride, px);
-        } else {
-            /* residuals of the 16 sub-blocks first: they do not depend on prediction */
-            int res[16];
-            bpred_residual(job, mb, lane, res);
-            uint4 *o = reinterpret_cast<uint4 *>(s_res[warp][lane]);
-            o[0] = make_uint4((res[0] & 0xffff) | (res[1] << 16), (res[2] & 0xffff) | (res[3] << 16),
-                              (res[4] & 0xffff) | (res[5] << 16), (res[6] & 0xffff) | (res[7] << 16));
-            o[1] = make_uint4((res[8] & 0xffff) | (res[9] << 16), (res[10] & 0xffff) | (res[11] << 16),
-                              (res[12] & 0xffff) | (res[13] << 16), (res[14] & 0xffff) | (res[15] << 16));
-        }
+        unsigned px[4];
+        block_mode(mb.y_mode, YT, YS, bx, by, dc_y, px);
+        if (has_res) add_res(px, res);
+        store4x4(dy + by * g.y_stride + bx, g.y_stride, px);
+        store4x4(YT + by * YS + bx, YS, px);
     }
     if (bpred) {
         /* 16 sub-blocks, anti-diagonal wavefront: block (br,bc) at step bc + 2*br needs left,
          * above and above-right (decodframe.c:200-237).  Two blocks per step at most: lanes
          * 0-15 are the pixels of the first, 16-31 of the second. */
-        const uint8_t *modes = reinterpret_cast<const uint8_t *>(job.aux + mb.u.aux);
-        const int pix = lane & 15, pr = pix >> 2, pc = pix & 3, which = lane >> 4;
         __syncwarp();
 #pragma unroll 1
         for (int step = 0; step < 10; step++) {
@@ -266,7 +307,7 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
             const bool act = br <= 3 && bc >= 0 && bc <= 3 && br <= (step >> 1);
             if (act) {
                 const int blk = br * 4 + bc;
-                const int mode = modes[blk];
+                const int mode = s_modes[warp][blk];
                 uint8_t *B = YT + br * 4 * YS + bc * 4;              /* block pixel (0,0) */
                 /* edge array element e: 0..3 = L3..L0, 4 = top-left, 5..12 = above / above-right;
                  * column 3 takes its above-right from row -1 of the MB (reconintra4x4.c:305-317) */
@@ -275,7 +316,7 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
                     if (e < 9) return B[-YS + e - 5];
                     return bc == 3 ? YT[-YS + 16 + e - 9] : B[-YS + e - 5];
                 };
-                const unsigned ent = c_bpred[mode][pix];
+                const unsigned ent = s_bpred[mode * 16 + pix];
                 const int kind = ent >> 12;
                 int v;
                 if (kind == 0) v = (E(ent & 15) + 2 * E((ent >> 4) & 15) + E((ent >> 8) & 15) + 2) >> 2;
@@ -293,9 +334,23 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
             *reinterpret_cast<uint4 *>(dy + lane * g.y_stride) = make_uint4(r[0], r[1], r[2], r[3]);
         }
     }
-    /* ---- publish: this macroblock's unfiltered reconstruction is final ---- */
+    /* ---- export bottom row + right column for the neighbours still to come ---- */
     __syncwarp();
-    if (lane == 0) st_release(job.done + mbi, epoch);
+    if (lane < 16) {
+        unsigned w;
+        if (lane < 4) w = *reinterpret_cast<const unsigned *>(YT + 15 * YS + 4 * lane);
+        else if (lane < 8) w = *reinterpret_cast<const unsigned *>((lane < 6 ? UT : VT) + 7 * CS + 4 * (lane & 1));
+        else if (lane < 12) {
+            const uint8_t *q = YT + (4 * (lane - 8)) * YS + 15;
+            w = q[0] | (q[YS] << 8) | (q[2 * YS] << 16) | ((unsigned)q[3 * YS] << 24);
+        } else {
+            const uint8_t *q = (lane < 14 ? UT : VT) + (4 * (lane & 1)) * CS + 7;
+            w = q[0] | (q[CS] << 8) | (q[2 * CS] << 16) | ((unsigned)q[3 * CS] << 24);
+        }
+        const unsigned long long v = ((unsigned long long)epoch << 32) | w;
+        unsigned long long *p = job.intra_msg + (size_t)mbi * 16 + lane;
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    }
 }
 
 void vp8b200_launch_intra(cudaStream_t s, const FrameJob *jobs, int n_jobs, const Geo &g,

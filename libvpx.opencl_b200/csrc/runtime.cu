@@ -56,7 +56,7 @@ struct vp8b200_ctx {
     int cur;
     bool open;
     vp8b200_frame_hdr cur_hdr;
-    unsigned *d_done;              /* per-MB intra "done" flags (epoch values) */
+    unsigned long long *d_imsg;    /* per-MB exported intra borders, 16 tagged words each */
     uint32_t *d_diag;              /* all MB indices sorted by wavefront index c + 2r */
     int *diag_tmp;                 /* host scratch for the counting sort */
     uint8_t *d_lfmsg;              /* loop-filter row hand-off messages, 256 B per MB */
@@ -135,7 +135,7 @@ static void free_ctx(vp8b200_ctx *c)
         cudaFreeHost(c->h_bjobs[i]); cudaFree(c->d_bjobs[i]);
         if (c->bjobs_done[i]) cudaEventDestroy(c->bjobs_done[i]);
     }
-    cudaFree(c->d_done); cudaFree(c->d_diag); cudaFree(c->d_tickets); cudaFree(c->d_lfmsg);
+    cudaFree(c->d_imsg); cudaFree(c->d_diag); cudaFree(c->d_tickets); cudaFree(c->d_lfmsg);
     free(c->diag_tmp);
     if (c->fetch_done) cudaEventDestroy(c->fetch_done);
     if (c->spans) {
@@ -197,8 +197,8 @@ static int create_impl(vp8b200_ctx *c)
         CK(c, cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
     }
     for (int i = 0; i < NBJOB; i++) CK(c, cudaEventCreateWithFlags(&c->bjobs_done[i], cudaEventDisableTiming));
-    CK(c, cudaMalloc((void **)&c->d_done, n_mb * sizeof(unsigned)));
-    CK(c, cudaMemsetAsync(c->d_done, 0, n_mb * sizeof(unsigned), c->stream));
+    CK(c, cudaMalloc((void **)&c->d_imsg, n_mb * 128));
+    CK(c, cudaMemsetAsync(c->d_imsg, 0, n_mb * 128, c->stream));
     CK(c, cudaMalloc((void **)&c->d_diag, n_mb * sizeof(uint32_t)));
     c->diag_tmp = (int *)malloc(sizeof(int) * (size_t)(g.mb_cols + 2 * g.mb_rows + 2));
     if (!c->diag_tmp) return VP8B200_ERR_NOMEM;
@@ -338,7 +338,7 @@ static void fill_job(vp8b200_ctx *c, FrameJob *j, const vp8b200_frame_hdr &h, co
     j->dst = c->fb[h.fb_new];
     j->ref[1] = c->fb[h.fb_last]; j->ref[2] = c->fb[h.fb_golden]; j->ref[3] = c->fb[h.fb_altref];
     j->mb = d_mb; j->aux = d_aux; j->coef = d_coef;
-    j->done = c->d_done;
+    j->intra_msg = c->d_imsg;
     j->intra_list = d_ilist ? d_ilist : c->d_diag;
     j->lf_msg = c->d_lfmsg;
     if (run_intra) c->epoch_intra++;

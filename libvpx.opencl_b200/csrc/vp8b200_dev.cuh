@@ -218,6 +218,59 @@ __device__ __forceinline__ void bpred_residual(const FrameJob &job, const vp8b20
     idct4x4(q, res);
 }
 
+/* Residual of block `blk` (0..23) as 16 values (zero when the block adds nothing), computed
+ * independently of the prediction: decodframe.c:252-304 / :217-236.  Returns true when any
+ * value may be non-zero. */
+__device__ __forceinline__ bool block_residual(const FrameJob &job, const vp8b200_mb &mb, int blk,
+                                               bool has_y2, int (&res)[16])
+{
+#pragma unroll
+    for (int i = 0; i < 16; i++) res[i] = 0;
+    if (mb.flags & VP8B200_MBF_SKIP) return false;
+    const int16_t(*dq)[2] = job.hdr.dequant[mb.flags & VP8B200_MBF_SEGMENT_MASK];
+    const unsigned mask = mb.coef_mask;
+    const bool present = (mask >> blk) & 1u;
+    const int plane = blk < 16 ? 0 : 2;
+    int dc_f = dq[plane][0];
+    const int ac_f = dq[plane][1];
+    int dc = 0;
+    const bool luma_y2 = has_y2 && blk < 16;
+    if (luma_y2) {
+        if (mask & (1u << 24)) {
+            const int16_t *y2 = job.coef + ((size_t)mb.coef_off + __popc(mask & 0xffffffu)) * 16;
+            dc = iwalsh_dc(y2, dq[1][0], dq[1][1], blk);
+        }
+        dc_f = 1;
+    }
+    if (present) {
+        int q[16];
+        load_coefs(job.coef + ((size_t)mb.coef_off + __popc(mask & ((1u << blk) - 1u))) * 16, q);
+        if (luma_y2) q[0] = dc;
+        q[0] = s16(q[0] * dc_f);
+#pragma unroll
+        for (int i = 1; i < 16; i++) q[i] = s16(q[i] * ac_f);
+        idct4x4(q, res);
+        return true;
+    }
+    if (luma_y2) {
+        const int a = (dc + 4) >> 3;                /* idct_blk.c:32-36 */
+#pragma unroll
+        for (int i = 0; i < 16; i++) res[i] = a;
+        return a != 0;
+    }
+    return false;
+}
+
+__device__ __forceinline__ void add_res(unsigned (&px)[4], const int (&res)[16])
+{
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const unsigned p = px[r];
+        px[r] = pack4(clamp255(res[4 * r] + (int)(p & 255)), clamp255(res[4 * r + 1] + (int)((p >> 8) & 255)),
+                      clamp255(res[4 * r + 2] + (int)((p >> 16) & 255)), clamp255(res[4 * r + 3] + (int)(p >> 24)));
+    }
+}
+
 __device__ __forceinline__ void store4x4(uint8_t *dst, int stride, const unsigned (&px)[4])
 {
 #pragma unroll

@@ -23,7 +23,7 @@ struct FrameJob {
     const vp8b200_mb *mb;
     const vp8b200_aux *aux;
     const int16_t *coef;
-    unsigned int *done;           /* per-MB "intra reconstruction finished" flags (= epoch)   */
+    unsigned long long *intra_msg; /* per-MB exported borders: 16 tagged 64-bit words          */
     const uint32_t *intra_list;   /* indices of the intra MBs, sorted by wavefront c + 2r     */
     uint8_t *lf_msg;              /* loop-filter row hand-off: 256 B per macroblock           */
     unsigned int epoch_intra;     /* progress values of this frame are (epoch << 13) + columns; */
