@@ -143,8 +143,9 @@ __device__ __forceinline__ BlkPos block_pos(const Geo &g, int lane, int mb_row, 
     return b;
 }
 
+/* SPLITMV macroblocks: one warp per MB, lane = 4x4 block with its own motion vector */
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-k_inter(const FrameJob *__restrict__ jobs, const Geo g)
+k_inter_split(const FrameJob *__restrict__ jobs, const Geo g)
 {
     __shared__ FrameJob job;
     {
@@ -153,13 +154,14 @@ k_inter(const FrameJob *__restrict__ jobs, const Geo g)
         for (int i = threadIdx.x; i < (int)(sizeof(FrameJob) / 4); i += blockDim.x) d[i] = s[i];
     }
     __syncthreads();
-    if (job.hdr.frame_type == 0) return;                       /* key frame: nothing inter */
+    if (job.hdr.frame_type == 0 || job.n_split == 0) return;   /* nothing to do in this frame */
     const int lane = threadIdx.x & 31;
     const int mbi = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
     if (mbi >= g.mb_cols * g.mb_rows) return;
     vp8b200_mb mb;
     *reinterpret_cast<uint4 *>(&mb) = __ldg(reinterpret_cast<const uint4 *>(job.mb + mbi));
     if (mb.ref_frame == VP8B200_INTRA_FRAME) return;           /* k_intra's */
+    if (mb.y_mode != VP8B200_SPLITMV) return;                  /* k_inter16's */
     const int mb_row = mbi / g.mb_cols, mb_col = mbi - mb_row * g.mb_cols;
     const bool active = lane < 24;
     const int blk = active ? lane : 0;
@@ -210,9 +212,214 @@ k_inter(const FrameJob *__restrict__ jobs, const Geo g)
     store4x4(job.dst + bp.off + bp.y * bp.stride + bp.x, bp.stride, px);
 }
 
-void vp8b200_launch_inter(cudaStream_t s, const FrameJob *jobs, int n_jobs, const Geo &g)
+
+/* ---------------------------------------------------------------------------------------
+ * k_inter16: macroblocks with ONE motion vector (everything except SPLITMV), the common case.
+ * Six lanes per macroblock, five macroblocks per warp: lanes 0-3 of a group own the four
+ * 4-pixel-wide luma column strips (16 rows), lanes 4-5 own the two chroma strips and do U
+ * then V (8 rows each).  A strip is walked top to bottom in units of four rows with a
+ * sliding 9-row window of first-pass results, so the horizontal pass runs over h+5 rows
+ * exactly once (21 for luma; 13 + 13 for chroma) instead of 9 rows per 4x4 block, and both
+ * passes use dp4a on byte-packed operands.  Residual (dequant + WHT + IDCT) is added per
+ * 4x4 block right before the block's four 32-bit row stores.
+ * ------------------------------------------------------------------------------------- */
+#define I16_WARPS 4
+#define I16_MB_PER_WARP 5
+
+/* DCs of the four luma blocks of column `col` from the second-order block (idctllm.c:140-192) */
+__device__ __forceinline__ void iwalsh_col(const int16_t *y2, int dc_f, int ac_f, int col, int (&dc)[4])
 {
-    dim3 grid((g.mb_cols * g.mb_rows + WARPS_PER_CTA - 1) / WARPS_PER_CTA, n_jobs);
-    k_inter<<<grid, WARPS_PER_CTA * 32, 0, s>>>(jobs, g);
+    int q[16];
+    load_coefs(y2, q);
+    q[0] = s16(q[0] * dc_f);
+#pragma unroll
+    for (int i = 1; i < 16; i++) q[i] = s16(q[i] * ac_f);
+    int mid[16];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int a = q[i] + q[12 + i];
+        int b = q[4 + i] + q[8 + i];
+        int c = q[4 + i] - q[8 + i];
+        int d = q[i] - q[12 + i];
+        mid[i] = s16(a + b);
+        mid[4 + i] = s16(c + d);
+        mid[8 + i] = s16(a - b);
+        mid[12 + i] = s16(d - c);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        int m0 = mid[4 * r], m1 = mid[4 * r + 1], m2 = mid[4 * r + 2], m3 = mid[4 * r + 3];
+        int a = m0 + m3, b = m1 + m2, c = m1 - m2, d = m0 - m3;
+        int o = col == 0 ? a + b : col == 1 ? c + d : col == 2 ? a - b : d - c;
+        dc[r] = s16((o + 3) >> 3);
+    }
 }
 
+/* residual of one block given the (optional) WHT DC; same arithmetic as add_residual */
+__device__ __forceinline__ void residual_dc(const FrameJob &job, const vp8b200_mb &mb, int blk, bool luma,
+                                            int dc, unsigned (&px)[4])
+{
+    const int16_t(*dq)[2] = job.hdr.dequant[mb.flags & VP8B200_MBF_SEGMENT_MASK];
+    const unsigned mask = mb.coef_mask;
+    if ((mask >> blk) & 1u) {
+        int q[16];
+        load_coefs(job.coef + ((size_t)mb.coef_off + __popc(mask & ((1u << blk) - 1u))) * 16, q);
+        const int plane = luma ? 0 : 2;
+        q[0] = luma ? dc : s16(q[0] * dq[plane][0]);      /* luma DC comes from the WHT, factor 1 */
+#pragma unroll
+        for (int i = 1; i < 16; i++) q[i] = s16(q[i] * dq[plane][1]);
+        idct4x4_add(q, px);
+    } else if (luma && dc != 0) {
+        dc_add(dc, px);
+    } else if (luma) {
+        /* (0 + 4) >> 3 == 0: nothing to add */
+    }
+}
+
+__global__ void __launch_bounds__(I16_WARPS * 32)
+k_inter16(const FrameJob *__restrict__ jobs, const Geo g)
+{
+    __shared__ FrameJob job;
+    {
+        const unsigned *s = reinterpret_cast<const unsigned *>(&jobs[blockIdx.y]);
+        unsigned *d = reinterpret_cast<unsigned *>(&job);
+        for (int i = threadIdx.x; i < (int)(sizeof(FrameJob) / 4); i += blockDim.x) d[i] = s[i];
+    }
+    __syncthreads();
+    if (job.hdr.frame_type == 0) return;                       /* key frame: nothing inter */
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gi = lane / 6, li = lane - gi * 6;               /* group (macroblock) and role */
+    const int n_mb = g.mb_cols * g.mb_rows;
+    const int mbi = (blockIdx.x * I16_WARPS + warp) * I16_MB_PER_WARP + gi;
+    bool active = gi < I16_MB_PER_WARP && mbi < n_mb;
+    vp8b200_mb mb;
+    *reinterpret_cast<uint4 *>(&mb) = active ? __ldg(reinterpret_cast<const uint4 *>(job.mb + mbi)) : make_uint4(0, 0, 0, 0);
+    active = active && mb.ref_frame != VP8B200_INTRA_FRAME && mb.y_mode != VP8B200_SPLITMV;
+    if (!__any_sync(FULL_MASK, active)) return;
+    const int mb_row = active ? mbi / g.mb_cols : 0, mb_col = active ? mbi - mb_row * g.mb_cols : 0;
+    const bool luma = li < 4;
+    const int strip = luma ? li : li - 4;
+
+    /* motion vector: reconinter.c:384-441 */
+    MV mv;
+    mv.row = active ? mb.u.mv.row : 0; mv.col = active ? mb.u.mv.col : 0;   /* idle lanes read (0,0) */
+    if (active && (mb.flags & VP8B200_MBF_CLAMP_MVS))
+        mv = clamp_mv(mv, -((mb_col * 16) << 3), ((g.mb_cols - 1 - mb_col) * 16) << 3,
+                      -((mb_row * 16) << 3), ((g.mb_rows - 1 - mb_row) * 16) << 3);
+    if (!luma) {                                               /* reconinter.c:419-424 */
+        const int fpmask = job.hdr.full_pixel ? ~7 : ~0;
+        mv.row = s16(mv.row + (1 | (mv.row >> 31)));
+        mv.col = s16(mv.col + (1 | (mv.col >> 31)));
+        mv.row = (mv.row / 2) & fpmask;
+        mv.col = (mv.col / 2) & fpmask;
+    }
+    const int xo = mv.col & 7, yo = mv.row & 7;
+    const int tb = job.hdr.use_bilinear_mc ? 8 : 0;
+    const int2 th = c_taps[tb + xo], tv = c_taps[tb + yo];
+    const bool idh = xo == 0, idv = yo == 0;
+    const bool need_v = __any_sync(FULL_MASK, active && yo != 0);
+
+    const int stride = luma ? g.y_stride : g.uv_stride;
+    const int wstride = stride >> 2;
+    const int px0 = (luma ? mb_col * 16 : mb_col * 8) + strip * 4;
+    const int py0 = luma ? mb_row * 16 : mb_row * 8;
+    const uint8_t *refbuf = job.ref[active ? mb.ref_frame : 1];
+    /* second-order transform once per luma lane */
+    const bool skip = (mb.flags & VP8B200_MBF_SKIP) != 0;
+    int dc4[4] = {0, 0, 0, 0};
+    if (active && luma && !skip && (mb.coef_mask & (1u << 24))) {
+        const int16_t(*dq)[2] = job.hdr.dequant[mb.flags & VP8B200_MBF_SEGMENT_MASK];
+        iwalsh_col(job.coef + ((size_t)mb.coef_off + __popc(mb.coef_mask & 0xffffffu)) * 16, dq[1][0], dq[1][1], strip, dc4);
+    }
+
+    unsigned c0[4], c1[4], c2[4];                              /* 9-row window, one column per index */
+    const unsigned *wp = nullptr;                              /* word holding pixel (x-2) of row 0 of the plane strip */
+    unsigned sh = 0;
+    uint8_t *dstp = nullptr;
+
+    /* one first-pass row into window slot W (compile-time) */
+#define HROW(ROWREL, W)                                                                         \
+    {                                                                                           \
+        const unsigned *row_ = wp + (ROWREL) * wstride;                                         \
+        const unsigned w0_ = __ldg(row_), w1_ = __ldg(row_ + 1), w2_ = __ldg(row_ + 2);         \
+        const unsigned v0_ = __funnelshift_r(w0_, w1_, sh), v1_ = __funnelshift_r(w1_, w2_, sh), v2_ = w2_ >> sh; \
+        _Pragma("unroll") for (int j_ = 0; j_ < 4; j_++) {                                      \
+            const unsigned lo_ = j_ ? __funnelshift_r(v0_, v1_, 8 * j_) : v0_;                  \
+            const unsigned hi_ = j_ ? __funnelshift_r(v1_, v2_, 8 * j_) : v1_;                  \
+            const unsigned f_ = (unsigned)filt6(lo_, hi_, th, idh);                             \
+            if ((W) < 4) c0[j_] = __byte_perm(c0[j_], f_, (W) == 0 ? 0x3214 : (W) == 1 ? 0x3240 : (W) == 2 ? 0x3410 : 0x4210); \
+            else if ((W) < 8) c1[j_] = __byte_perm(c1[j_], f_, (W) == 4 ? 0x3214 : (W) == 5 ? 0x3240 : (W) == 6 ? 0x3410 : 0x4210); \
+            else c2[j_] = f_;                                                                   \
+        }                                                                                       \
+    }
+
+#pragma unroll 1
+    for (int u = 0; u < 4; u++) {
+        const bool start = u == 0 || (!luma && u == 2);        /* first unit of a plane strip */
+        const int ur = luma ? u : (u & 1);                     /* unit index inside the plane */
+        if (start) {
+            const int poff = luma ? g.y_off : (u < 2 ? g.u_off : g.v_off);
+            const uint8_t *p = refbuf + poff + (size_t)(py0 + (mv.row >> 3)) * stride + px0 + (mv.col >> 3) - 2;
+            sh = ((unsigned)(uintptr_t)p & 3u) * 8u;
+            wp = reinterpret_cast<const unsigned *>(p - (sh >> 3));
+            dstp = job.dst + poff + (size_t)py0 * stride + px0;
+        }
+        unsigned px[4];
+        if (need_v) {
+            if (start) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) { c0[j] = 0; c1[j] = 0; c2[j] = 0; }
+                HROW(-2, 0) HROW(-1, 1) HROW(0, 2) HROW(1, 3) HROW(2, 4)
+            }
+            const unsigned *wsave = wp;
+            wp += (4 * ur) * wstride;
+            HROW(3, 5) HROW(4, 6) HROW(5, 7) HROW(6, 8)
+            wp = wsave;
+            int o[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const unsigned lo = r ? __funnelshift_r(c0[j], c1[j], 8 * r) : c0[j];
+                    const unsigned hi = r ? __funnelshift_r(c1[j], c2[j], 8 * r) : c1[j];
+                    o[r][j] = filt6(lo, hi, tv, idv);
+                }
+#pragma unroll
+            for (int r = 0; r < 4; r++) px[r] = pack4(o[r][0], o[r][1], o[r][2], o[r][3]);
+            /* slide the window down four rows */
+#pragma unroll
+            for (int j = 0; j < 4; j++) { c0[j] = c1[j]; c1[j] = c2[j]; }
+        } else {
+            /* no lane has a vertical fraction: the second pass is the identity */
+            const unsigned *wsave = wp;
+            wp += (4 * ur) * wstride;
+            HROW(0, 0) HROW(1, 1) HROW(2, 2) HROW(3, 3)
+            wp = wsave;
+            /* c0[j] holds column j: transpose to rows */
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                px[r] = pack4((c0[0] >> (8 * r)) & 255, (c0[1] >> (8 * r)) & 255, (c0[2] >> (8 * r)) & 255, (c0[3] >> (8 * r)) & 255);
+        }
+        if (active) {
+            if (!skip) {
+                const int blk = luma ? 4 * u + strip : (u < 2 ? 16 : 20) + 2 * ur + strip;
+                const int dcu = u == 0 ? dc4[0] : u == 1 ? dc4[1] : u == 2 ? dc4[2] : dc4[3];
+                residual_dc(job, mb, blk, luma, luma ? dcu : 0, px);
+            }
+            store4x4(dstp + (size_t)(4 * ur) * stride, stride, px);
+        }
+    }
+#undef HROW
+}
+
+void vp8b200_launch_inter(cudaStream_t s, const FrameJob *jobs, int n_jobs, const Geo &g, bool any_split)
+{
+    const int n_mb = g.mb_cols * g.mb_rows;
+    const int per_cta = I16_WARPS * I16_MB_PER_WARP;
+    dim3 grid16((n_mb + per_cta - 1) / per_cta, n_jobs);
+    k_inter16<<<grid16, I16_WARPS * 32, 0, s>>>(jobs, g);
+    if (any_split) {
+        dim3 grid((n_mb + WARPS_PER_CTA - 1) / WARPS_PER_CTA, n_jobs);
+        k_inter_split<<<grid, WARPS_PER_CTA * 32, 0, s>>>(jobs, g);
+    }
+}

@@ -41,7 +41,7 @@ struct vp8b200_staged {
     vp8b200_aux *d_aux;
     int16_t *d_coef;
     uint32_t *d_ilist;             /* NULL on key frames: the context's static order is used */
-    unsigned n_intra;
+    unsigned n_intra, n_split;
 };
 
 struct vp8b200_ctx {
@@ -332,7 +332,7 @@ static bool records_ok(const Geo &g, const vp8b200_mb *mb, const vp8b200_aux *au
 
 static void fill_job(vp8b200_ctx *c, FrameJob *j, const vp8b200_frame_hdr &h, const vp8b200_mb *d_mb,
                      const vp8b200_aux *d_aux, const int16_t *d_coef, const uint32_t *d_ilist,
-                     unsigned n_intra, bool run_intra, bool run_lf)
+                     unsigned n_intra, unsigned n_split, bool run_intra, bool run_lf)
 {
     memset(j, 0, sizeof *j);
     j->dst = c->fb[h.fb_new];
@@ -346,6 +346,7 @@ static void fill_job(vp8b200_ctx *c, FrameJob *j, const vp8b200_frame_hdr &h, co
     j->epoch_intra = c->epoch_intra;
     j->epoch_lf = c->epoch_lf;
     j->n_intra = n_intra;
+    j->n_split = n_split;
     j->hdr = h;
 }
 
@@ -363,15 +364,23 @@ static void prof_mark(vp8b200_ctx *c, int kind, bool begin)
     }
 }
 
-static int run_jobs(vp8b200_ctx *c, const FrameJob *d_jobs, int n, bool any_inter, unsigned max_intra, bool any_lf)
+static unsigned count_split(const vp8b200_mb *mb, uint32_t n)
+{
+    unsigned k = 0;
+    for (uint32_t i = 0; i < n; i++) k += mb[i].y_mode == VP8B200_SPLITMV;
+    return k;
+}
+
+static int run_jobs(vp8b200_ctx *c, const FrameJob *d_jobs, int n, bool any_inter, bool any_split,
+                    unsigned max_intra, bool any_lf)
 {
     const bool any_intra = max_intra > 0;
     int nctas = 0;
     unsigned k = 0;
     if (any_inter) {
         prof_mark(c, 0, true);
-        vp8b200_launch_inter(c->stream, d_jobs, n, c->geo);
-        prof_mark(c, 0, false); k++;
+        vp8b200_launch_inter(c->stream, d_jobs, n, c->geo, any_split);
+        prof_mark(c, 0, false); k += any_split ? 2 : 1;
     }
     if (any_intra) {
         prof_mark(c, 1, true);
@@ -411,7 +420,8 @@ extern "C" int vp8b200_frame_submit(vp8b200_ctx *c, uint32_t n_aux, uint32_t n_c
     /* key frames use the context's static wavefront order; P frames list their intra MBs */
     const unsigned n_intra = key ? c->n_mb : wavefront_order(c->geo, s.h_mb, c->n_mb, s.h_ilist, c->diag_tmp);
     const bool run_intra = n_intra > 0, run_lf = h.filter_level != 0;
-    fill_job(c, s.h_job, h, s.d_mb, s.d_aux, s.d_coef, key ? NULL : s.d_ilist, n_intra, run_intra, run_lf);
+    const unsigned n_split = key ? 0 : count_split(s.h_mb, c->n_mb);
+    fill_job(c, s.h_job, h, s.d_mb, s.d_aux, s.d_coef, key ? NULL : s.d_ilist, n_intra, n_split, run_intra, run_lf);
     if (!key && n_intra)
         CK(c, cudaMemcpyAsync(s.d_ilist, s.h_ilist, (size_t)n_intra * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     CK(c, cudaMemcpyAsync(s.d_mb, s.h_mb, (size_t)c->n_mb * sizeof(vp8b200_mb), cudaMemcpyHostToDevice, c->stream));
@@ -422,7 +432,7 @@ extern "C" int vp8b200_frame_submit(vp8b200_ctx *c, uint32_t n_aux, uint32_t n_c
     s.pending = true;
     g_h2d_bytes += (uint64_t)c->n_mb * sizeof(vp8b200_mb) + (uint64_t)n_aux * sizeof(vp8b200_aux) +
                    (uint64_t)n_coef * 32 + sizeof(FrameJob) + (key ? 0 : (uint64_t)n_intra * 4);
-    int st = run_jobs(c, s.d_job, 1, !key, n_intra, run_lf);
+    int st = run_jobs(c, s.d_job, 1, !key, n_split > 0, n_intra, run_lf);
     c->cur = (c->cur + 1) % NSLOT;
     return st;
 }
@@ -509,6 +519,7 @@ extern "C" int vp8b200_stage_frame(vp8b200_ctx *c, const vp8b200_frame_hdr *hdr,
     s->d_aux = (vp8b200_aux *)(s->d_blob + mb_pad);
     s->d_coef = (int16_t *)(s->d_blob + mb_pad + aux_b);
     s->n_intra = n_intra;
+    s->n_split = key ? 0 : count_split(mb, c->n_mb);
     s->d_ilist = key ? NULL : (uint32_t *)(s->d_blob + mb_pad + aux_b + coef_pad);
     if (!key && n_intra) {
         cudaError_t e2 = cudaMemcpy(s->d_ilist, ilist, (size_t)n_intra * 4, cudaMemcpyHostToDevice);
@@ -556,11 +567,11 @@ extern "C" int vp8b200_batch_run(vp8b200_ctx *const *ctx, vp8b200_staged *const 
     }
     const int r = c->bjobs_cur;
     if (c->bjobs_pending[r]) { CK(c, cudaEventSynchronize(c->bjobs_done[r])); c->bjobs_pending[r] = false; }
-    bool any_inter = false, any_lf = false;
+    bool any_inter = false, any_lf = false, any_split = false;
     unsigned max_intra = 0;
     for (int i = 0; i < n; i++) {
         const vp8b200_staged *s = frame[i];
-        any_inter |= s->hdr.frame_type != 0; any_lf |= s->hdr.filter_level != 0;
+        any_inter |= s->hdr.frame_type != 0; any_lf |= s->hdr.filter_level != 0; any_split |= s->n_split > 0;
         if (s->n_intra > max_intra) max_intra = s->n_intra;
     }
     for (int i = 0; i < n; i++) {
@@ -568,14 +579,14 @@ extern "C" int vp8b200_batch_run(vp8b200_ctx *const *ctx, vp8b200_staged *const 
         /* a context's intra / loop-filter epoch advances only when that kernel really has
          * work for it (done flags and message tags of idle jobs stay untouched) */
         fill_job(ctx[i], &c->h_bjobs[r][i], s->hdr, s->d_mb, s->d_aux, s->d_coef, s->d_ilist, s->n_intra,
-                 s->n_intra > 0, any_lf && s->hdr.filter_level != 0);
+                 s->n_split, s->n_intra > 0, any_lf && s->hdr.filter_level != 0);
     }
     CK(c, cudaMemcpyAsync(c->d_bjobs[r], c->h_bjobs[r], (size_t)n * sizeof(FrameJob), cudaMemcpyHostToDevice, c->stream));
     g_h2d_bytes += (uint64_t)n * sizeof(FrameJob);
     CK(c, cudaEventRecord(c->bjobs_done[r], c->stream));
     c->bjobs_pending[r] = true;
     c->bjobs_cur = (r + 1) % NBJOB;
-    return run_jobs(c, c->d_bjobs[r], n, any_inter, max_intra, any_lf);
+    return run_jobs(c, c->d_bjobs[r], n, any_inter, any_split, max_intra, any_lf);
 }
 
 /* ---- statistics and per-kernel profiling -------------------------------------------------- */

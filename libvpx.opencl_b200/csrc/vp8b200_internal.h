@@ -29,6 +29,7 @@ struct FrameJob {
     unsigned int epoch_intra;     /* progress values of this frame are (epoch << 13) + columns; */
     unsigned int epoch_lf;        /* each counter advances only when its kernel really runs     */
     unsigned int n_intra;         /* intra macroblocks in the frame (0 => intra kernel idle)  */
+    unsigned int n_split;         /* SPLITMV macroblocks in the frame                         */
     vp8b200_frame_hdr hdr;
 };
 
@@ -39,7 +40,7 @@ void vp8b200_upload_intra_constants();  /* B_PRED predictor table */
 
 /* launch wrappers (kernels_*.cu); `tickets` points at two device counters owned by the
  * launching context, ticket_base = value of the counter before this launch */
-void vp8b200_launch_inter(cudaStream_t s, const FrameJob *jobs, int n_jobs, const Geo &g);
+void vp8b200_launch_inter(cudaStream_t s, const FrameJob *jobs, int n_jobs, const Geo &g, bool any_split);
 void vp8b200_launch_intra(cudaStream_t s, const FrameJob *jobs, int n_jobs, const Geo &g,
                           unsigned int max_intra, unsigned int *ticket, unsigned int ticket_base,
                           int *n_ctas);
