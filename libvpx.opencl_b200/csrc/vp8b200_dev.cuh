@@ -200,24 +200,6 @@ __device__ __forceinline__ void idct4x4(const int (&in)[16], int (&out)[16])
     }
 }
 
-/* Residual of a B_PRED luma sub-block (no Y2): 16 values, all zero when the block carries
- * no coefficients (decodframe.c:217-236). */
-__device__ __forceinline__ void bpred_residual(const FrameJob &job, const vp8b200_mb &mb, int blk, int (&res)[16])
-{
-#pragma unroll
-    for (int i = 0; i < 16; i++) res[i] = 0;
-    if (mb.flags & VP8B200_MBF_SKIP) return;
-    const unsigned mask = mb.coef_mask;
-    if (!((mask >> blk) & 1u)) return;
-    const int16_t(*dq)[2] = job.hdr.dequant[mb.flags & VP8B200_MBF_SEGMENT_MASK];
-    int q[16];
-    load_coefs(job.coef + ((size_t)mb.coef_off + __popc(mask & ((1u << blk) - 1u))) * 16, q);
-    q[0] = s16(q[0] * dq[0][0]);
-#pragma unroll
-    for (int i = 1; i < 16; i++) q[i] = s16(q[i] * dq[0][1]);
-    idct4x4(q, res);
-}
-
 /* Residual of block `blk` (0..23) as 16 values (zero when the block adds nothing), computed
  * independently of the prediction: decodframe.c:252-304 / :217-236.  Returns true when any
  * value may be non-zero. */
@@ -275,17 +257,6 @@ __device__ __forceinline__ void store4x4(uint8_t *dst, int stride, const unsigne
 {
 #pragma unroll
     for (int r = 0; r < 4; r++) *reinterpret_cast<unsigned *>(dst + r * stride) = px[r];
-}
-
-__device__ __forceinline__ unsigned ld_acquire(const unsigned *p)
-{
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release(unsigned *p, unsigned v)
-{
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 #endif
