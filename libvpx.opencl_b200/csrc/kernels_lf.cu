@@ -129,13 +129,14 @@ __device__ __forceinline__ void g_send(uint8_t *slot, const unsigned (&m)[4], un
 __device__ __forceinline__ void g_recv(const uint8_t *slot, unsigned (&m)[4], unsigned tag, bool luma)
 {
     unsigned long long a, b, c = 0, d = 0;
+    int tries = 0;
     for (;;) {
         ld_msg2(slot, a, b);
         if (luma) ld_msg2(slot + 16, c, d);
         bool ok = (unsigned)(a >> 32) == tag && (unsigned)(b >> 32) == tag;
         if (luma) ok = ok && (unsigned)(c >> 32) == tag && (unsigned)(d >> 32) == tag;
         if (ok) break;
-        __nanosleep(200);
+        if (++tries > 8) __nanosleep(100);
     }
     m[0] = (unsigned)a; m[1] = (unsigned)b; m[2] = (unsigned)c; m[3] = (unsigned)d;
 }
@@ -312,7 +313,7 @@ k_loopfilter(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g,
         /* ---- the 4 rows above arrive as a message from the row above ---- */
         if (top) {
             if (recv_smem) {
-                while (s_sent[warp - 1] <= (unsigned)c) { }
+                for (int tries = 0; s_sent[warp - 1] <= (unsigned)c; tries++) if (tries > 24) __nanosleep(64);   /* spin briefly, then back off */
                 __threadfence_block();
                 if (receiver) {
                     const uint8_t *slot = s_ring[warp - 1][c & (LF_RING - 1)] + sr_off;
