@@ -28,6 +28,7 @@
 
 #define LF_ROWS_PER_CTA 4
 #define LF_RING 4                 /* shared-memory message slots per row (power of two) */
+#define LF_PF 3                   /* prefetch distance in macroblocks */
 
 __device__ __forceinline__ int sc(int v) { return max(min(v, 127), -128); }
 __device__ __forceinline__ int ad(int a, int b) { return __sad(a, b, 0); }      /* |a-b|, one VABSDIFF */
@@ -220,11 +221,20 @@ k_loopfilter(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g,
     const int sr_off = luma ? pi * 16 : (lane < 24 ? 64 : 96) + pi * 8;
 
     const unsigned *mbrec = reinterpret_cast<const unsigned *>(job.mb + (size_t)mb_row * g.mb_cols);
-    unsigned cur[4] = {0, 0, 0, 0}, nxt[4] = {0, 0, 0, 0}, prev[3] = {0, 0, 0}, halo = 0;
-    if (lane_on) {
-        if (luma) { uint4 v = *reinterpret_cast<const uint4 *>(rowp); cur[0] = v.x; cur[1] = v.y; cur[2] = v.z; cur[3] = v.w; }
-        else { uint2 v = *reinterpret_cast<const uint2 *>(rowp); cur[0] = v.x; cur[1] = v.y; }
-    }
+    /* pixel rows are prefetched LF_PF macroblocks ahead: under load the DRAM/L2 latency of a
+     * row is several iterations long */
+    unsigned cur[4] = {0, 0, 0, 0}, pf[LF_PF][4], prev[3] = {0, 0, 0}, halo = 0;
+    auto load_row = [&](int col, unsigned (&d)[4]) {
+        if (lane_on && col < g.mb_cols) {
+            if (luma) { uint4 v = *reinterpret_cast<const uint4 *>(rowp + col * 16); d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+            else { uint2 v = *reinterpret_cast<const uint2 *>(rowp + col * 8); d[0] = v.x; d[1] = v.y; }
+        }
+    };
+#pragma unroll
+    for (int i = 0; i < LF_PF; i++) { pf[i][0] = pf[i][1] = pf[i][2] = pf[i][3] = 0; }
+    load_row(0, cur);
+#pragma unroll
+    for (int i = 0; i < LF_PF - 1; i++) load_row(i + 1, pf[i]);
     unsigned rec = mbrec[0], rec_n = 0;
 
     /* message for MB `col` of this row: words of rows keep.. after the next MB's left edge */
@@ -248,14 +258,9 @@ k_loopfilter(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g,
     };
 
     for (int c = 0; c < g.mb_cols; c++) {
-        /* prefetch the next macroblock's rows and record */
-        if (c + 1 < g.mb_cols) {
-            rec_n = mbrec[(c + 1) * 4];
-            if (lane_on) {
-                if (luma) { uint4 v = *reinterpret_cast<const uint4 *>(rowp + (c + 1) * 16); nxt[0] = v.x; nxt[1] = v.y; nxt[2] = v.z; nxt[3] = v.w; }
-                else { uint2 v = *reinterpret_cast<const uint2 *>(rowp + (c + 1) * 8); nxt[0] = v.x; nxt[1] = v.y; }
-            }
-        }
+        /* prefetch: the record of the next macroblock, the rows of the one LF_PF ahead */
+        if (c + 1 < g.mb_cols) rec_n = mbrec[(c + 1) * 4];
+        load_row(c + LF_PF, pf[LF_PF - 1]);
         /* per-MB decisions, loopfilter.c:245-253 */
         const int y_mode = rec & 255, ref = (rec >> 16) & 255, flags = rec >> 24;
         const bool skip_lf = y_mode != VP8B200_B_PRED && y_mode != VP8B200_SPLITMV && (flags & VP8B200_MBF_SKIP);
@@ -404,7 +409,11 @@ k_loopfilter(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g,
         __syncwarp();                                       /* tile is reused by the next MB */
         rec = rec_n;
 #pragma unroll
-        for (int i = 0; i < 4; i++) cur[i] = nxt[i];
+        for (int i = 0; i < 4; i++) {
+            cur[i] = pf[0][i];
+#pragma unroll
+            for (int k = 0; k + 1 < LF_PF; k++) pf[k][i] = pf[k + 1][i];
+        }
     }
     /* last 4 columns of the row */
     if (owns_store) *reinterpret_cast<unsigned *>(rowp + g.mb_cols * mbw - 4) = halo;
