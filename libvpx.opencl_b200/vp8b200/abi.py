@@ -9,7 +9,8 @@ import numpy as np
 from .recfile import HDR_DTYPE, MB_DTYPE
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libvp8b200.so")
+# VP8B200_LIB selects another build of the same library (A/B experiments); default = in-tree build
+LIB_PATH = os.environ.get("VP8B200_LIB") or os.path.join(os.path.dirname(_HERE), "libvp8b200.so")
 
 EXPORTS = [
     "vp8b200_abi_version", "vp8b200_strerror", "vp8b200_last_error", "vp8b200_device_count",
