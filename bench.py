@@ -162,9 +162,19 @@ def run_b200(args):
     gstaged = [[[staged[f][s] for s in idx] for idx in gidx] for f in range(F)]
     gstreams = [torch.cuda.ExternalStream(gc[0].stream(), device=dev) for gc in gctx]
 
+    # ctypes argument arrays are built once, not per step (the timed loop is launch-rate sensitive)
+    import ctypes as C
+    L = abi.lib()
+    g_ca = [(C.c_void_p * len(gc))(*[c.h for c in gc]) for gc in gctx]
+    g_sa = [[(C.c_void_p * len(gstaged[f][gi]))(*gstaged[f][gi]) for gi in range(G)] for f in range(F)]
+    g_n = [len(gc) for gc in gctx]
+
     def step(i):
+        f = i % F
         for gi in range(G):
-            abi.batch_run(gctx[gi], gstaged[i % F][gi])
+            st = L.vp8b200_batch_run(g_ca[gi], g_sa[f][gi], g_n[gi])
+            if st:
+                raise SystemExit("bench: vp8b200_batch_run failed: %d" % st)
 
     def sync_all():
         for gc in gctx:
