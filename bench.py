@@ -245,8 +245,12 @@ def run_b200(args):
     pred_ms = prof["inter"][0] + prof["intra"][0]
     kern["pred_GBps"] = round(pred_bytes / (pred_ms / 1e3) / 1e9, 1) if pred_ms else None
     achieved = lf_bytes / (lf_ms / 1e3) / 1e9 if lf_ms else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):                    # dram bytes per launch from the committed ncu capture
+        traffic = json.load(open(tpath)).get("k_loopfilter", {}).get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "kernel": "k_loopfilter", "achieved": round(achieved, 1), "peak": peak,
-                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                 "peak_source": peak_src, "bytes_per_launch": round(lf_bytes / max(lf_n, 1)),
                 "ms_per_launch": round(lf_ms / max(lf_n, 1), 4), "kernels": kern}
 
