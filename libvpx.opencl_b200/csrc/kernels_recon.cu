@@ -33,28 +33,31 @@ void vp8b200_upload_constants()
     static const int bil[8][2] = {{128, 0}, {112, 16}, {96, 32}, {80, 48},
                                   {64, 64}, {48, 80},  {32, 96}, {16, 112}};
     int2 h[16];
-    /* 128 does not fit a signed byte: the identity / full-weight tap is applied as -128 and
-     * the sum negated (see filt6), so store tap values t with the 128 case flagged by
-     * keeping -128 in the byte. */
+    /* .x multiplies window bytes 0..3, .y multiplies window bytes 2..5 (so .y = {*, 0, t4, t5}).
+     * 128 does not fit a signed byte: the full-weight tap is split as 127 in .x plus 1 on the
+     * same pixel (byte 2 of the window = byte 0 of the .y operand). */
     for (int i = 0; i < 8; i++) {
-        h[i].x = pack_s8(six[i][0], six[i][1], six[i][2] == 128 ? -128 : six[i][2], six[i][3]);
-        h[i].y = pack_s8(six[i][4], six[i][5], 0, 0);
-        h[8 + i].x = pack_s8(0, 0, bil[i][0] == 128 ? -128 : bil[i][0], bil[i][1]);
-        h[8 + i].y = 0;
+        const int s2 = six[i][2] == 128 ? 127 : six[i][2], s2b = six[i][2] == 128 ? 1 : 0;
+        h[i].x = pack_s8(six[i][0], six[i][1], s2, six[i][3]);
+        h[i].y = pack_s8(s2b, 0, six[i][4], six[i][5]);
+        const int b2 = bil[i][0] == 128 ? 127 : bil[i][0], b2b = bil[i][0] == 128 ? 1 : 0;
+        h[8 + i].x = pack_s8(0, 0, b2, bil[i][1]);
+        h[8 + i].y = pack_s8(b2b, 0, 0, 0);
     }
     cudaMemcpyToSymbol(c_taps, h, sizeof h);
 }
 
-/* One six-tap evaluation on 8 consecutive bytes lo (p0..p3) / hi (p4..p7).
- * Fraction 0 is the only filter with a 128 tap; its packed byte is -128, so the dot product
- * comes out as -128*p2 and is negated.  Result: clamp((sum + 64) >> 7). */
-__device__ __forceinline__ int filt6(unsigned lo, unsigned hi, int2 t, bool identity)
+/* One six-tap evaluation: lo = window bytes 0..3, mid = window bytes 2..5 (see the tap table).
+ * Result: clamp(((sum) + 64) >> 7); the rounding constant rides in the dp4a accumulator. */
+__device__ __forceinline__ int filt6(unsigned lo, unsigned mid, int2 t)
 {
-    int s = dp4a_us(lo, t.x, 0);
-    s = dp4a_us(hi, t.y, s);
-    s = identity ? -s : s;
-    return clamp255((s + 64) >> 7);
+    int s = dp4a_us(lo, t.x, 64);
+    s = dp4a_us(mid, t.y, s);
+    return clamp255(s >> 7);
 }
+/* window bytes 2..5 for output j of a row held as v0 = bytes 0..3, v1 = 4..7, v2 = 8.. */
+#define WIN_LO(v0, v1, j) ((j) ? __funnelshift_r((v0), (v1), 8 * (j)) : (v0))
+#define WIN_MID(v0, v1, v2, j) ((j) < 2 ? __funnelshift_r((v0), (v1), 8 * ((j) + 2)) : (j) == 2 ? (v1) : __funnelshift_r((v1), (v2), 8))
 
 struct MV { int row, col; };
 
@@ -86,7 +89,6 @@ __device__ __forceinline__ void predict4x4(const uint8_t *src, int stride, int x
                                            bool need_v, unsigned (&px)[4])
 {
     const int2 th = c_taps[tb + xo], tv = c_taps[tb + yo];
-    const bool idh = xo == 0, idv = yo == 0;
     /* the 9 source bytes x-2 .. x+6 of a row live in 3 aligned words */
     const uint8_t *p = src - 2;
     unsigned sh = ((unsigned)(uintptr_t)p & 3u) * 8u;
@@ -105,9 +107,7 @@ __device__ __forceinline__ void predict4x4(const uint8_t *src, int stride, int x
         unsigned v2 = w2 >> sh;                         /* p8 ..  */
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            unsigned lo = j ? __funnelshift_r(v0, v1, 8 * j) : v0;
-            unsigned hi = j ? __funnelshift_r(v1, v2, 8 * j) : v1;
-            unsigned f = (unsigned)filt6(lo, hi, th, idh);
+            unsigned f = (unsigned)filt6(WIN_LO(v0, v1, j), WIN_MID(v0, v1, v2, j), th);
             if (r < 4) c0[j] |= f << (8 * r);
             else if (r < 8) c1[j] |= f << (8 * (r - 4));
             else c2[j] = f;
@@ -119,9 +119,7 @@ __device__ __forceinline__ void predict4x4(const uint8_t *src, int stride, int x
     for (int j = 0; j < 4; j++)
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-            unsigned lo = r ? __funnelshift_r(c0[j], c1[j], 8 * r) : c0[j];
-            unsigned hi = r ? __funnelshift_r(c1[j], c2[j], 8 * r) : c1[j];
-            o[r][j] = filt6(lo, hi, tv, idv);
+            o[r][j] = filt6(WIN_LO(c0[j], c1[j], r), WIN_MID(c0[j], c1[j], c2[j], r), tv);
         }
 #pragma unroll
     for (int r = 0; r < 4; r++) px[r] = pack4(o[r][0], o[r][1], o[r][2], o[r][3]);
@@ -316,7 +314,6 @@ k_inter16(const FrameJob *__restrict__ jobs, const Geo g)
     const int xo = mv.col & 7, yo = mv.row & 7;
     const int tb = job.hdr.use_bilinear_mc ? 8 : 0;
     const int2 th = c_taps[tb + xo], tv = c_taps[tb + yo];
-    const bool idh = xo == 0, idv = yo == 0;
     const bool need_v = __any_sync(FULL_MASK, active && yo != 0);
 
     const int stride = luma ? g.y_stride : g.uv_stride;
@@ -344,9 +341,7 @@ k_inter16(const FrameJob *__restrict__ jobs, const Geo g)
         const unsigned w0_ = __ldg(row_), w1_ = __ldg(row_ + 1), w2_ = __ldg(row_ + 2);         \
         const unsigned v0_ = __funnelshift_r(w0_, w1_, sh), v1_ = __funnelshift_r(w1_, w2_, sh), v2_ = w2_ >> sh; \
         _Pragma("unroll") for (int j_ = 0; j_ < 4; j_++) {                                      \
-            const unsigned lo_ = j_ ? __funnelshift_r(v0_, v1_, 8 * j_) : v0_;                  \
-            const unsigned hi_ = j_ ? __funnelshift_r(v1_, v2_, 8 * j_) : v1_;                  \
-            const unsigned f_ = (unsigned)filt6(lo_, hi_, th, idh);                             \
+            const unsigned f_ = (unsigned)filt6(WIN_LO(v0_, v1_, j_), WIN_MID(v0_, v1_, v2_, j_), th); \
             if ((W) < 4) c0[j_] = __byte_perm(c0[j_], f_, (W) == 0 ? 0x3214 : (W) == 1 ? 0x3240 : (W) == 2 ? 0x3410 : 0x4210); \
             else if ((W) < 8) c1[j_] = __byte_perm(c1[j_], f_, (W) == 4 ? 0x3214 : (W) == 5 ? 0x3240 : (W) == 6 ? 0x3410 : 0x4210); \
             else c2[j_] = f_;                                                                   \
@@ -380,9 +375,7 @@ k_inter16(const FrameJob *__restrict__ jobs, const Geo g)
             for (int j = 0; j < 4; j++)
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
-                    const unsigned lo = r ? __funnelshift_r(c0[j], c1[j], 8 * r) : c0[j];
-                    const unsigned hi = r ? __funnelshift_r(c1[j], c2[j], 8 * r) : c1[j];
-                    o[r][j] = filt6(lo, hi, tv, idv);
+                    o[r][j] = filt6(WIN_LO(c0[j], c1[j], r), WIN_MID(c0[j], c1[j], c2[j], r), tv);
                 }
 #pragma unroll
             for (int r = 0; r < 4; r++) px[r] = pack4(o[r][0], o[r][1], o[r][2], o[r][3]);
