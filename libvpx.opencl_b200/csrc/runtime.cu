@@ -72,6 +72,13 @@ struct vp8b200_ctx {
     cudaEvent_t fetch_done;
     bool profiling;
     std::vector<ProfSpan> *spans;
+    /* cross-stream ordering between a context's own stream and a batch leader's stream */
+    cudaEvent_t own_ev;            /* recorded on this context's stream when a batch must wait for it */
+    bool own_dirty;                /* work queued on the own stream since the last batch / sync */
+    cudaEvent_t batch_ev;          /* event of the batch (on the leader's stream) that last touched this context */
+    bool batch_pending;            /* own stream has not yet waited for batch_ev */
+    vp8b200_ctx *batch_leader;     /* whose stream that batch ran on */
+    cudaEvent_t lead_ev[NBJOB];    /* as a leader: one event per in-flight batch */
     char err[256];
 };
 
@@ -134,7 +141,9 @@ static void free_ctx(vp8b200_ctx *c)
     for (int i = 0; i < NBJOB; i++) {
         cudaFreeHost(c->h_bjobs[i]); cudaFree(c->d_bjobs[i]);
         if (c->bjobs_done[i]) cudaEventDestroy(c->bjobs_done[i]);
+        if (c->lead_ev[i]) cudaEventDestroy(c->lead_ev[i]);
     }
+    if (c->own_ev) cudaEventDestroy(c->own_ev);
     cudaFree(c->d_imsg); cudaFree(c->d_diag); cudaFree(c->d_tickets); cudaFree(c->d_lfmsg);
     free(c->diag_tmp);
     if (c->fetch_done) cudaEventDestroy(c->fetch_done);
@@ -196,7 +205,11 @@ static int create_impl(vp8b200_ctx *c)
         CK(c, cudaMalloc((void **)&s.d_ilist, n_mb * sizeof(uint32_t)));
         CK(c, cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
     }
-    for (int i = 0; i < NBJOB; i++) CK(c, cudaEventCreateWithFlags(&c->bjobs_done[i], cudaEventDisableTiming));
+    for (int i = 0; i < NBJOB; i++) {
+        CK(c, cudaEventCreateWithFlags(&c->bjobs_done[i], cudaEventDisableTiming));
+        CK(c, cudaEventCreateWithFlags(&c->lead_ev[i], cudaEventDisableTiming));
+    }
+    CK(c, cudaEventCreateWithFlags(&c->own_ev, cudaEventDisableTiming));
     CK(c, cudaMalloc((void **)&c->d_imsg, n_mb * 128));
     CK(c, cudaMemsetAsync(c->d_imsg, 0, n_mb * 128, c->stream));
     CK(c, cudaMalloc((void **)&c->d_diag, n_mb * sizeof(uint32_t)));
@@ -267,6 +280,17 @@ extern "C" size_t vp8b200_frame_size(const vp8b200_ctx *ctx) { return ctx ? ctx-
 extern "C" int vp8b200_y_stride(const vp8b200_ctx *ctx) { return ctx ? ctx->geo.y_stride : 0; }
 extern "C" uint64_t vp8b200_launch_count(const vp8b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" void *vp8b200_stream(const vp8b200_ctx *ctx) { return ctx ? (void *)ctx->stream : NULL; }
+
+/* A context that took part in vp8b200_batch_run was written by kernels on the LEADER's stream;
+ * make its own stream wait for that batch before queueing anything on it. */
+static int join_batch(vp8b200_ctx *c)
+{
+    if (c->batch_pending) {
+        CK(c, cudaStreamWaitEvent(c->stream, c->batch_ev, 0));
+        c->batch_pending = false;
+    }
+    return VP8B200_OK;
+}
 
 static bool hdr_ok(const vp8b200_ctx *c, const vp8b200_frame_hdr *h)
 {
@@ -410,6 +434,8 @@ extern "C" int vp8b200_frame_submit(vp8b200_ctx *c, uint32_t n_aux, uint32_t n_c
     c->open = false;
     if (n_aux > c->n_mb || n_coef > c->n_mb * 25) return VP8B200_ERR_OVERFLOW;
     CK(c, cudaSetDevice(c->device));
+    { int js = join_batch(c); if (js) return js; }
+    c->own_dirty = true;
     Slot &s = c->slot[c->cur];
     const vp8b200_frame_hdr &h = c->cur_hdr;
     const bool key = h.frame_type == 0;
@@ -441,6 +467,7 @@ extern "C" int vp8b200_frame_fetch(vp8b200_ctx *c, int fb, uint8_t *dst, size_t 
 {
     if (!c || fb < 0 || fb >= c->n_fb || !dst || bytes > c->frame_size) return VP8B200_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
+    { int js = join_batch(c); if (js) return js; }
     CK(c, cudaMemcpyAsync(dst, c->fb[fb], bytes, cudaMemcpyDeviceToHost, c->stream));
     if (c->blocking_sync) {
         CK(c, cudaEventRecord(c->fetch_done, c->stream));
@@ -456,6 +483,7 @@ extern "C" int vp8b200_frame_upload(vp8b200_ctx *c, int fb, const uint8_t *src, 
 {
     if (!c || fb < 0 || fb >= c->n_fb || !src || bytes > c->frame_size) return VP8B200_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
+    { int js = join_batch(c); if (js) return js; }
     CK(c, cudaMemcpyAsync(c->fb[fb], src, bytes, cudaMemcpyHostToDevice, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return VP8B200_OK;
@@ -466,6 +494,8 @@ extern "C" int vp8b200_frame_copy(vp8b200_ctx *c, int fb_dst, int fb_src)
     if (!c || fb_dst < 0 || fb_dst >= c->n_fb || fb_src < 0 || fb_src >= c->n_fb) return VP8B200_ERR_INVALID;
     if (fb_dst == fb_src) return VP8B200_OK;
     CK(c, cudaSetDevice(c->device));
+    { int js = join_batch(c); if (js) return js; }
+    c->own_dirty = true;
     CK(c, cudaMemcpyAsync(c->fb[fb_dst], c->fb[fb_src], c->frame_size, cudaMemcpyDeviceToDevice, c->stream));
     return VP8B200_OK;
 }
@@ -474,7 +504,9 @@ extern "C" int vp8b200_sync(vp8b200_ctx *c)
 {
     if (!c) return VP8B200_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
+    { int js = join_batch(c); if (js) return js; }
     CK(c, cudaStreamSynchronize(c->stream));
+    c->own_dirty = false;
     return VP8B200_OK;
 }
 
@@ -567,6 +599,19 @@ extern "C" int vp8b200_batch_run(vp8b200_ctx *const *ctx, vp8b200_staged *const 
     }
     const int r = c->bjobs_cur;
     if (c->bjobs_pending[r]) { CK(c, cudaEventSynchronize(c->bjobs_done[r])); c->bjobs_pending[r] = false; }
+    /* order the batch after whatever the members queued on their own streams, and after the
+     * batch (possibly under another leader) that last touched them */
+    { int js = join_batch(c); if (js) return js; }
+    for (int i = 1; i < n; i++) {
+        vp8b200_ctx *m = ctx[i];
+        if (m->batch_pending && m->batch_leader != c)       /* same leader = same stream: already ordered */
+            CK(c, cudaStreamWaitEvent(c->stream, m->batch_ev, 0));
+        if (m->own_dirty) {
+            CK(c, cudaEventRecord(m->own_ev, m->stream));
+            CK(c, cudaStreamWaitEvent(c->stream, m->own_ev, 0));
+            m->own_dirty = false;
+        }
+    }
     bool any_inter = false, any_lf = false, any_split = false;
     unsigned max_intra = 0;
     for (int i = 0; i < n; i++) {
@@ -586,7 +631,11 @@ extern "C" int vp8b200_batch_run(vp8b200_ctx *const *ctx, vp8b200_staged *const 
     CK(c, cudaEventRecord(c->bjobs_done[r], c->stream));
     c->bjobs_pending[r] = true;
     c->bjobs_cur = (r + 1) % NBJOB;
-    return run_jobs(c, c->d_bjobs[r], n, any_inter, any_split, max_intra, any_lf);
+    int st = run_jobs(c, c->d_bjobs[r], n, any_inter, any_split, max_intra, any_lf);
+    if (st) return st;
+    CK(c, cudaEventRecord(c->lead_ev[r], c->stream));
+    for (int i = 1; i < n; i++) { ctx[i]->batch_ev = c->lead_ev[r]; ctx[i]->batch_pending = true; ctx[i]->batch_leader = c; }
+    return VP8B200_OK;
 }
 
 /* ---- statistics and per-kernel profiling -------------------------------------------------- */

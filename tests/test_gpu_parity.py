@@ -157,3 +157,33 @@ def test_1080p_round_trip_properties(gpu_lib):
     y1, u1, v1 = geo.planes(ctx.fetch(2))
     assert np.array_equal(y0, y1) and np.array_equal(u0, u1) and np.array_equal(v0, v1)
     ctx.close()
+
+
+def test_batch_then_individual_use_is_ordered(gpu_lib):
+    """A member of a batch is written on the leader's stream; fetching it through its own
+    context right away (no explicit sync) must still see the finished frame, and a frame
+    submitted individually must be visible to a following batch."""
+    n_streams, mb_cols, mb_rows = 6, 40, 30
+    w, h = mb_cols * 16, mb_rows * 16
+    geo = frames.Geometry(w, h)
+    rng = np.random.default_rng(123)
+    ctxs = [abi.Context(w, h, 4) for _ in range(n_streams)]
+    oras = [OracleDecoder(w, h, 4) for _ in range(n_streams)]
+    for c, o in zip(ctxs, oras):
+        for fb, buf in enumerate(randrec.random_buffers(rng, geo.frame_size, 4)):
+            c.upload(fb, buf)
+            o.fb(fb)[:] = buf
+    # 1) individual submit on every context, immediately followed by a batch that predicts from it
+    f0 = [randrec.random_frame(rng, mb_cols, mb_rows, fbs=(0, 1, 2, 3)) for _ in range(n_streams)]
+    for c, o, fr in zip(ctxs, oras, f0):
+        c.submit(fr)
+        o.frame(fr)
+    f1 = [randrec.random_frame(rng, mb_cols, mb_rows, p_intra=0.05, fbs=(1, 0, 0, 0)) for _ in range(n_streams)]
+    staged = [c.stage(fr) for c, fr in zip(ctxs, f1)]
+    abi.batch_run(ctxs, staged)
+    # 2) no sync: fetch members through their own contexts
+    for s in reversed(range(n_streams)):
+        oras[s].frame(f1[s])
+        _compare(ctxs[s].fetch(1), oras[s].fb(1), geo, "ordered batch stream %d" % s)
+    for c in ctxs:
+        c.close()
