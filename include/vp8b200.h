@@ -186,7 +186,11 @@ int  vp8b200_stage_frame(vp8b200_ctx *ctx, const vp8b200_frame_hdr *hdr,
                          const int16_t *coef, uint32_t n_coef, vp8b200_staged **out);
 void vp8b200_staged_free(vp8b200_ctx *ctx, vp8b200_staged *s);
 /* Reconstruct frame[i] on ctx[i] for i < n with ONE launch of each kernel covering all n
- * streams (all contexts must share device and geometry).  Asynchronous on ctx[0]'s stream. */
+ * streams (all contexts must share device and geometry).  Asynchronous on ctx[0]'s stream
+ * (the "leader").  Ordering is handled by the library: the batch waits for work the members
+ * queued on their own streams, and a member's later frame_submit / frame_fetch / sync waits
+ * for the batch.  A staged frame may be replayed any number of times and on any context of
+ * the same geometry. */
 int  vp8b200_batch_run(vp8b200_ctx *const *ctx, vp8b200_staged *const *frame, int n);
 
 /* process-wide monotonic counters: [0] bytes copied host->device, [1] device->host,

@@ -26,6 +26,10 @@
 #include "vp8b200_dev.cuh"
 
 #define INTRA_WARPS 4
+#ifndef INTRA_SPIN
+#define INTRA_SPIN 0
+#define INTRA_SLEEP 32
+#endif
 #define YS 48             /* luma tile pitch: rows -1..15, cols -16..31 ; index (r+1)*48 + 16 + c */
 #define CS 16             /* chroma tile pitch: rows -1..7, cols -4..11 ; index (r+1)*16 + 4 + c  */
 
@@ -212,10 +216,10 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
                     const int word = grp == 0 ? 8 + j : (grp == 1 ? j : (grp == 2 ? 3 + 2 * j : 0));
                     const unsigned long long *p = msg + (size_t)ni * 16 + word;
                     unsigned long long v;
-                    for (;;) {
+                    for (int tries = 0;; tries++) {
                         asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
                         if ((unsigned)(v >> 32) == epoch) break;
-                        __nanosleep(32);
+                        if (tries > INTRA_SPIN) __nanosleep(INTRA_SLEEP);   /* poll hard first: the hand-off is on the chain */
                     }
                     w = (unsigned)v;
                 } else if (grp == 0) {
