@@ -129,6 +129,7 @@ static void free_ctx(vp8b200_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->batch_pending) cudaEventSynchronize(c->batch_ev);   /* a batch on another leader's stream may still use us */
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (int i = 0; i < c->n_fb; i++) cudaFree(c->fb[i]);
     for (int i = 0; i < NSLOT; i++) {
@@ -571,7 +572,8 @@ extern "C" int vp8b200_stage_frame(vp8b200_ctx *c, const vp8b200_frame_hdr *hdr,
 extern "C" void vp8b200_staged_free(vp8b200_ctx *c, vp8b200_staged *s)
 {
     if (!s) return;
-    if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+    /* a staged frame can be in flight on any leader's stream: teardown path, wait for the device */
+    if (c) { cudaSetDevice(c->device); cudaDeviceSynchronize(); }
     cudaFree(s->d_blob);
     delete s;
 }
