@@ -48,6 +48,9 @@ def p_decodframe(l):
     # S2: frame begin replaces the 127/129 edge setup (device applies the rule itself)
     i = find_one(l, "vp8_setup_intra_recon(&pc->yv12_fb[pc->new_fb_idx]);")
     l[i] = "        vp8b200_seam_frame_begin(pbi);\n"
+    # S3a: tokens are read straight into the coefficient arena
+    i = find_one(l, "eobtotal = vp8_decode_mb_tokens(pbi, xd);")
+    l[i] = l[i].replace("vp8_decode_mb_tokens", "vp8b200_seam_decode_tokens")
     # S3: per-MB record replaces prediction + residual
     i = find_one(l, "/* do prediction */")
     l.insert(i, "    vp8b200_seam_record_mb(pbi, xd, mb_idx);\n    return;\n")

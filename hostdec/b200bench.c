@@ -36,6 +36,26 @@ static pthread_barrier_t g_bar;
 static double g_t0, g_t1[1024];
 static long g_frames[1024];
 static uint64_t g_checksum;
+static double g_cpu_dec[1024], g_cpu_get[1024];   /* thread CPU seconds inside the two API calls */
+static double g_runq[1024];                        /* seconds a worker sat runnable without a core */
+
+/* /proc/thread-self/schedstat: "<on-cpu ns> <run-queue wait ns> <timeslices>" */
+static double runq_s(void)
+{
+    FILE *f = fopen("/proc/thread-self/schedstat", "r");
+    unsigned long long cpu = 0, wait = 0;
+    if (!f) return 0;
+    if (fscanf(f, "%llu %llu", &cpu, &wait) != 2) wait = 0;
+    fclose(f);
+    return 1e-9 * (double)wait;
+}
+
+static double cpu_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
 
 static double now_s(void)
 {
@@ -73,17 +93,19 @@ static void load_clip(clip_t *c, const char *path)
     }
 }
 
-static long decode_one(inst_t *in, int f, uint64_t *sum)
+static long decode_one(inst_t *in, int f, uint64_t *sum, double *cpu)
 {
     const clip_t *c = in->clip;
     vpx_codec_iter_t it = NULL;
     vpx_image_t *img;
     long shown = 0;
+    double c0 = cpu ? cpu_s() : 0, c1;
     if (vpx_codec_decode(&in->dec, c->data + c->off[f], c->len[f], NULL, 0)) {
         fprintf(stderr, "decode failed: %s (%s)\n", vpx_codec_error(&in->dec),
                 vpx_codec_error_detail(&in->dec) ? vpx_codec_error_detail(&in->dec) : "");
         exit(3);
     }
+    if (cpu) { c1 = cpu_s(); cpu[0] += c1 - c0; c0 = c1; }
     while ((img = vpx_codec_get_frame(&in->dec, &it))) {
         shown++;
         if (sum) {
@@ -105,6 +127,7 @@ static long decode_one(inst_t *in, int f, uint64_t *sum)
             (void)t;
         }
     }
+    if (cpu) cpu[1] += cpu_s() - c0;
     return shown;
 }
 
@@ -112,6 +135,7 @@ static void *worker(void *arg)
 {
     int t = (int)(intptr_t)arg, i, f, r, maxf = 0;
     long n = 0;
+    double cpu[2] = {0, 0};
     for (i = t; i < g_streams; i += g_threads) {
         vpx_codec_dec_cfg_t cfg = {0};
         inst_t *in = &g_inst[i];
@@ -122,16 +146,19 @@ static void *worker(void *arg)
     /* warm-up pass (untimed): creates the device contexts, pins memory */
     for (f = 0; f < maxf; f++)
         for (i = t; i < g_streams; i += g_threads)
-            if (f < g_inst[i].clip->nframes) decode_one(&g_inst[i], f, NULL);
+            if (f < g_inst[i].clip->nframes) decode_one(&g_inst[i], f, NULL, NULL);
     pthread_barrier_wait(&g_bar);
     if (t == 0) g_t0 = now_s();
     pthread_barrier_wait(&g_bar);
+    g_runq[t] = -runq_s();
     for (r = 0; r < g_repeat; r++)
         for (f = 0; f < maxf; f++)
             for (i = t; i < g_streams; i += g_threads)
                 if (f < g_inst[i].clip->nframes)
-                    n += decode_one(&g_inst[i], f, (g_sum && i == 0 && r == g_repeat - 1) ? &g_checksum : NULL);
+                    n += decode_one(&g_inst[i], f, (g_sum && i == 0 && r == g_repeat - 1) ? &g_checksum : NULL, cpu);
     g_t1[t] = now_s();
+    g_cpu_dec[t] = cpu[0]; g_cpu_get[t] = cpu[1];
+    g_runq[t] += runq_s();
     g_frames[t] = n;
     pthread_barrier_wait(&g_bar);
     for (i = t; i < g_streams; i += g_threads) vpx_codec_destroy(&g_inst[i].dec);
@@ -145,6 +172,7 @@ int main(int argc, char **argv)
     long total = 0;
     double tend = 0;
     uint64_t st0[4], st1[4];
+    double cpu_dec = 0, cpu_get = 0, runq = 0, thread_wall = 0;
     for (i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--threads") && i + 1 < argc) g_threads = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--streams") && i + 1 < argc) g_streams = atoi(argv[++i]);
@@ -163,16 +191,23 @@ int main(int argc, char **argv)
     vp8b200_global_stats(st0);
     for (i = 0; i < g_threads; i++) pthread_join(th[i], NULL);
     vp8b200_global_stats(st1);
-    for (i = 0; i < g_threads; i++) { total += g_frames[i]; if (g_t1[i] > tend) tend = g_t1[i]; }
+    for (i = 0; i < g_threads; i++) {
+        total += g_frames[i]; cpu_dec += g_cpu_dec[i]; cpu_get += g_cpu_get[i];
+        runq += g_runq[i]; thread_wall += g_t1[i] - g_t0;
+        if (g_t1[i] > tend) tend = g_t1[i];
+    }
     {
         /* warm-up = 1 pass, timed = g_repeat passes: per-frame byte counts are identical */
         double share = (double)g_repeat / (double)(g_repeat + 1);
         printf("{\"frames\": %ld, \"wall_s\": %.6f, \"fps\": %.3f, \"threads\": %d, \"streams\": %d, "
                "\"repeat\": %d, \"h2d_bytes\": %.0f, \"d2h_bytes\": %.0f, \"kernel_launches\": %.0f, "
-               "\"checksum\": %llu}\n",
+               "\"cpu_ms_per_frame_decode\": %.4f, \"cpu_ms_per_frame_get_frame\": %.4f, "
+               "\"runq_wait_ms_per_frame\": %.4f, \"blocked_ms_per_frame\": %.4f, \"checksum\": %llu}\n",
                total, tend - g_t0, total / (tend - g_t0), g_threads, g_streams, g_repeat,
                (double)(st1[0] - st0[0]) * share, (double)(st1[1] - st0[1]) * share,
-               (double)(st1[2] - st0[2]) * share, (unsigned long long)g_checksum);
+               (double)(st1[2] - st0[2]) * share, 1e3 * cpu_dec / (total ? total : 1),
+               1e3 * cpu_get / (total ? total : 1), 1e3 * runq / (total ? total : 1),
+               1e3 * (thread_wall - cpu_dec - cpu_get - runq) / (total ? total : 1), (unsigned long long)g_checksum);
     }
     return 0;
 }

@@ -10,6 +10,7 @@
  *
  * Seams (reference file:line -> function here):
  *   vp8/decoder/decodframe.c:1064  vp8_setup_intra_recon      -> vp8b200_seam_frame_begin
+ *   vp8/decoder/decodframe.c:127   vp8_decode_mb_tokens       -> vp8b200_seam_decode_tokens
  *   vp8/decoder/decodframe.c:191   "do prediction" .. :304    -> vp8b200_seam_record_mb
  *   vp8/decoder/decodframe.c:430   vp8_extend_mb_row          -> (dropped; device rule)
  *   vp8/decoder/onyxd_if.c:576-607 loop filter + extend       -> vp8b200_seam_frame_submit
@@ -22,6 +23,8 @@
  *   VP8B200_DEVICE=<n>     CUDA device ordinal (default 0)
  *   VP8B200_DUMP=<path>    also write every frame's records to a .rec file
  *                          (include/vp8b200_recfile.h); "%p" in the path -> decoder address
+ *   VP8B200_TOKENS=ref     keep the reference's vp8_decode_mb_tokens + qcoeff scan instead of
+ *                          the fused token reader (vp8b200_tokens.c); for A/B tests
  *   VP8B200_NO_DEVICE=1    record-capture only: no device is touched and NO pixels are
  *                          produced (frames handed back are undefined).  Exists so that
  *                          golden .rec fixtures can be produced on a machine without a GPU;
@@ -40,6 +43,8 @@
 #include "vp8b200.h"
 #include "vp8b200_recfile.h"
 #include "vp8b200_seam.h"
+#include "vp8b200_tokens.h"
+#include "vp8/decoder/detokenize.h"
 
 typedef struct seam_state {
     vp8b200_ctx *ctx;
@@ -53,6 +58,9 @@ typedef struct seam_state {
     vp8b200_frame_bufs bufs;
     uint32_t n_aux, n_coef;
     int overflow;
+    int ref_tokens;               /* VP8B200_TOKENS=ref */
+    int tok_valid;                /* tok_off/tok_mask describe the current macroblock */
+    uint32_t tok_off, tok_mask;
     /* host-memory record buffers for VP8B200_NO_DEVICE */
     vp8b200_mb *h_mb; vp8b200_aux *h_aux; int16_t *h_coef;
 } seam_state;
@@ -74,6 +82,8 @@ static seam_state *seam_get(VP8D_COMP *pbi)
         if (!s) vpx_internal_error(&pbi->common.error, VPX_CODEC_MEM_ERROR, "vp8b200: seam state");
         e = getenv("VP8B200_NO_DEVICE");
         s->no_device = e && atoi(e);
+        e = getenv("VP8B200_TOKENS");
+        s->ref_tokens = e && !strcmp(e, "ref");
         e = getenv("VP8B200_DUMP");
         if (e && *e) {
             char path[1024];
@@ -204,8 +214,38 @@ void vp8b200_seam_frame_begin(VP8D_COMP *pbi)
         s->bufs.mb = s->h_mb; s->bufs.aux = s->h_aux; s->bufs.coef = s->h_coef;
         s->bufs.aux_capacity = n_mb; s->bufs.coef_capacity = 25 * n_mb;
     }
-    s->n_aux = 0; s->n_coef = 0; s->overflow = 0;
+    s->n_aux = 0; s->n_coef = 0; s->overflow = 0; s->tok_valid = 0;
     s->open = 1;
+}
+
+/* Called from decode_macroblock (vp8/decoder/decodframe.c:127) in place of
+ * vp8_decode_mb_tokens: reads the macroblock's tokens straight into the coefficient arena.
+ * Returns eobtotal like the function it replaces. */
+int vp8b200_seam_decode_tokens(VP8D_COMP *pbi, MACROBLOCKD *xd)
+{
+    seam_state *s = (seam_state *)pbi->b200_seam;
+    BOOL_DECODER *bc = xd->current_bc;
+    const int mode = xd->mode_info_context->mbmi.mode;
+    int16_t scratch[25 * 16];
+    int16_t *dst;
+    vp8b200_booldec bd;
+    uint32_t mask = 0;
+    int eobtotal;
+
+    if (!s || !s->open || s->ref_tokens) return vp8_decode_mb_tokens(pbi, xd);
+    if (s->n_coef + 25 > s->bufs.coef_capacity) { s->overflow = 1; dst = scratch; }
+    else dst = s->bufs.coef + (size_t)s->n_coef * 16;
+    bd.buf = bc->user_buffer; bd.buf_end = bc->user_buffer_end;
+    bd.value = bc->value; bd.count = bc->count; bd.range = bc->range;
+    eobtotal = vp8b200_decode_mb_tokens(&bd, &pbi->common.fc.coef_probs[0][0][0][0],
+                                        (signed char *)xd->above_context, (signed char *)xd->left_context,
+                                        mode != B_PRED && mode != SPLITMV, dst, &mask);
+    bc->user_buffer = bd.buf; bc->value = bd.value; bc->count = bd.count; bc->range = bd.range;
+    s->tok_off = s->n_coef;
+    s->tok_mask = s->overflow ? 0 : mask;
+    if (!s->overflow) s->n_coef += (uint32_t)__builtin_popcount(mask);
+    s->tok_valid = 1;
+    return eobtotal;
 }
 
 /* Called from decode_macroblock (vp8/decoder/decodframe.c) once tokens are decoded and
@@ -251,7 +291,11 @@ void vp8b200_seam_record_mb(VP8D_COMP *pbi, MACROBLOCKD *xd, unsigned int mb_idx
         r->u.mv.col = mbmi->mv.as_mv.col;
     }
 
-    if (!skip) {
+    if (!s->ref_tokens) {
+        /* the fused token reader already stored this macroblock's blocks */
+        if (s->tok_valid) { r->coef_off = s->tok_off; r->coef_mask = s->tok_mask; }
+        s->tok_valid = 0;
+    } else if (!skip) {
         /* eobs semantics: detokenize.c:183-384.  Y blocks of a Y2 macroblock start at
          * position 1, so they carry coefficients only when eob > 1. */
         uint32_t mask = 0;

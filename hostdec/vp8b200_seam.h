@@ -9,6 +9,7 @@ void *vp8b200_seam_alloc(size_t bytes);
 void  vp8b200_seam_free(void *p);
 void  vp8b200_seam_destroy(struct VP8D_COMP *pbi);
 void  vp8b200_seam_frame_begin(struct VP8D_COMP *pbi);
+int   vp8b200_seam_decode_tokens(struct VP8D_COMP *pbi, struct macroblockd *xd);
 void  vp8b200_seam_record_mb(struct VP8D_COMP *pbi, struct macroblockd *xd, unsigned int mb_idx);
 void  vp8b200_seam_frame_submit(struct VP8D_COMP *pbi);
 void  vp8b200_seam_fetch(struct VP8D_COMP *pbi);
