@@ -324,34 +324,59 @@ extern "C" int vp8b200_frame_abort(vp8b200_ctx *c)
     return VP8B200_OK;
 }
 
-/* validate what the kernels will index with (a corrupt record must not become a wild read) */
-static bool records_ok(const Geo &g, const vp8b200_mb *mb, const vp8b200_aux *aux, uint32_t n_mb,
-                       uint32_t n_aux, uint32_t n_coef, bool key)
+/* One pass over the frame's records at submit time: validates what the kernels will index
+ * with (a corrupt record must not become a wild read), counts SPLITMV macroblocks, and - for
+ * P frames - builds the wavefront order of the intra macroblocks (counting sort on
+ * d = col + 2*row, see wavefront_order).  Returns false on an invalid record. */
+static bool scan_records(const Geo &g, const vp8b200_mb *mb, const vp8b200_aux *aux, uint32_t n_aux,
+                         uint32_t n_coef, bool key, uint32_t *ilist, int *cnt, unsigned *n_intra_out,
+                         unsigned *n_split_out)
 {
-    for (uint32_t i = 0; i < n_mb; i++) {
-        const vp8b200_mb &m = mb[i];
-        if (m.y_mode > VP8B200_SPLITMV || m.uv_mode > VP8B200_TM_PRED || m.ref_frame > 3) return false;
-        bool intra = m.ref_frame == VP8B200_INTRA_FRAME;
-        if (intra != (m.y_mode <= VP8B200_B_PRED)) return false;
-        if (key && !intra) return false;
-        if ((m.y_mode == VP8B200_B_PRED || m.y_mode == VP8B200_SPLITMV) && m.u.aux >= n_aux) return false;
-        if (!intra && !(m.flags & VP8B200_MBF_CLAMP_MVS)) {
-            /* an unclamped MV must already be inside the range clamp_mv_to_umv_border
-             * (reconinter.c:348-368) leaves alone, or the 32-pixel border would not cover
-             * the filter window */
-            const int row = (int)(i / (uint32_t)g.mb_cols), col = (int)(i % (uint32_t)g.mb_cols);
-            const int lo_c = -((col * 16) << 3) - (19 << 3), hi_c = (((g.mb_cols - 1 - col) * 16) << 3) + (18 << 3);
-            const int lo_r = -((row * 16) << 3) - (19 << 3), hi_r = (((g.mb_rows - 1 - row) * 16) << 3) + (18 << 3);
-            const int nmv = m.y_mode == VP8B200_SPLITMV ? 16 : 1;
-            for (int k = 0; k < nmv; k++) {
-                int r = nmv == 1 ? m.u.mv.row : aux[m.u.aux].mv[k].row;
-                int c = nmv == 1 ? m.u.mv.col : aux[m.u.aux].mv[k].col;
-                if (r < lo_r || r > hi_r || c < lo_c || c > hi_c) return false;
+    const int nd = g.mb_cols + 2 * g.mb_rows;
+    unsigned n_intra = 0, n_split = 0;
+    if (!key) for (int d = 0; d <= nd; d++) cnt[d] = 0;
+    const vp8b200_mb *m = mb;
+    for (int row = 0; row < g.mb_rows; row++) {
+        /* range clamp_mv_to_umv_border (reconinter.c:348-368) leaves alone: an unclamped MV
+         * must already be inside it, or the 32-pixel border would not cover the filter window */
+        const int lo_r = -((row * 16) << 3) - (19 << 3), hi_r = (((g.mb_rows - 1 - row) * 16) << 3) + (18 << 3);
+        for (int col = 0; col < g.mb_cols; col++, m++) {
+            if (m->y_mode > VP8B200_SPLITMV || m->uv_mode > VP8B200_TM_PRED || m->ref_frame > 3) return false;
+            const bool intra = m->ref_frame == VP8B200_INTRA_FRAME;
+            if (intra != (m->y_mode <= VP8B200_B_PRED)) return false;
+            if (key && !intra) return false;
+            const bool has_aux = m->y_mode == VP8B200_B_PRED || m->y_mode == VP8B200_SPLITMV;
+            if (has_aux && m->u.aux >= n_aux) return false;
+            if (intra) {
+                if (!key) cnt[col + 2 * row + 1]++;
+                n_intra++;
+            } else {
+                const bool split = m->y_mode == VP8B200_SPLITMV;
+                n_split += split;
+                if (!(m->flags & VP8B200_MBF_CLAMP_MVS)) {
+                    const int lo_c = -((col * 16) << 3) - (19 << 3), hi_c = (((g.mb_cols - 1 - col) * 16) << 3) + (18 << 3);
+                    const int nmv = split ? 16 : 1;
+                    for (int k = 0; k < nmv; k++) {
+                        const int r = split ? aux[m->u.aux].mv[k].row : m->u.mv.row;
+                        const int c = split ? aux[m->u.aux].mv[k].col : m->u.mv.col;
+                        if (r < lo_r || r > hi_r || c < lo_c || c > hi_c) return false;
+                    }
+                }
             }
+            if (m->coef_mask >> 25) return false;
+            if (m->coef_mask && (uint64_t)m->coef_off + (unsigned)__builtin_popcount(m->coef_mask) > n_coef) return false;
         }
-        if (m.coef_mask >> 25) return false;
-        if (m.coef_mask && (uint64_t)m.coef_off + (unsigned)__builtin_popcount(m.coef_mask) > n_coef) return false;
     }
+    if (!key && n_intra) {
+        for (int d = 0; d < nd; d++) cnt[d + 1] += cnt[d];
+        m = mb;
+        uint32_t i = 0;
+        for (int row = 0; row < g.mb_rows; row++)
+            for (int col = 0; col < g.mb_cols; col++, m++, i++)
+                if (m->ref_frame == VP8B200_INTRA_FRAME) ilist[cnt[col + 2 * row]++] = i;
+    }
+    *n_intra_out = n_intra;
+    *n_split_out = n_split;
     return true;
 }
 
@@ -387,13 +412,6 @@ static void prof_mark(vp8b200_ctx *c, int kind, bool begin)
     } else {
         cudaEventRecord(c->spans->back().b, c->stream);
     }
-}
-
-static unsigned count_split(const vp8b200_mb *mb, uint32_t n)
-{
-    unsigned k = 0;
-    for (uint32_t i = 0; i < n; i++) k += mb[i].y_mode == VP8B200_SPLITMV;
-    return k;
 }
 
 static int run_jobs(vp8b200_ctx *c, const FrameJob *d_jobs, int n, bool any_inter, bool any_split,
@@ -440,14 +458,13 @@ extern "C" int vp8b200_frame_submit(vp8b200_ctx *c, uint32_t n_aux, uint32_t n_c
     Slot &s = c->slot[c->cur];
     const vp8b200_frame_hdr &h = c->cur_hdr;
     const bool key = h.frame_type == 0;
-    if (!records_ok(c->geo, s.h_mb, s.h_aux, c->n_mb, n_aux, n_coef, key)) {
+    /* key frames use the context's static wavefront order; P frames list their intra MBs */
+    unsigned n_intra = 0, n_split = 0;
+    if (!scan_records(c->geo, s.h_mb, s.h_aux, n_aux, n_coef, key, s.h_ilist, c->diag_tmp, &n_intra, &n_split)) {
         snprintf(c->err, sizeof c->err, "macroblock records failed validation");
         return VP8B200_ERR_INVALID;
     }
-    /* key frames use the context's static wavefront order; P frames list their intra MBs */
-    const unsigned n_intra = key ? c->n_mb : wavefront_order(c->geo, s.h_mb, c->n_mb, s.h_ilist, c->diag_tmp);
     const bool run_intra = n_intra > 0, run_lf = h.filter_level != 0;
-    const unsigned n_split = key ? 0 : count_split(s.h_mb, c->n_mb);
     fill_job(c, s.h_job, h, s.d_mb, s.d_aux, s.d_coef, key ? NULL : s.d_ilist, n_intra, n_split, run_intra, run_lf);
     if (!key && n_intra)
         CK(c, cudaMemcpyAsync(s.d_ilist, s.h_ilist, (size_t)n_intra * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
@@ -520,25 +537,25 @@ extern "C" int vp8b200_stage_frame(vp8b200_ctx *c, const vp8b200_frame_hdr *hdr,
     if (!c || !hdr || !mb || !out || !hdr_ok(c, hdr) || (n_aux && !aux) || (n_coef && !coef))
         return VP8B200_ERR_INVALID;
     if (n_aux > c->n_mb || n_coef > c->n_mb * 25) return VP8B200_ERR_OVERFLOW;
-    if (!records_ok(c->geo, mb, aux, c->n_mb, n_aux, n_coef, hdr->frame_type == 0)) {
+    const bool key = hdr->frame_type == 0;
+    uint32_t *ilist = NULL;
+    unsigned n_intra = 0, n_split = 0;
+    if (!key) {
+        ilist = (uint32_t *)malloc((size_t)c->n_mb * sizeof(uint32_t));
+        if (!ilist) return VP8B200_ERR_NOMEM;
+    }
+    if (!scan_records(c->geo, mb, aux, n_aux, n_coef, key, ilist, c->diag_tmp, &n_intra, &n_split)) {
         snprintf(c->err, sizeof c->err, "macroblock records failed validation");
+        free(ilist);
         return VP8B200_ERR_INVALID;
     }
-    CK(c, cudaSetDevice(c->device));
+    { cudaError_t e0 = cudaSetDevice(c->device); if (e0 != cudaSuccess) { free(ilist); CK(c, e0); } }
     vp8b200_staged *s = new (std::nothrow) vp8b200_staged();
-    if (!s) return VP8B200_ERR_NOMEM;
+    if (!s) { free(ilist); return VP8B200_ERR_NOMEM; }
     const size_t mb_b = (size_t)c->n_mb * sizeof(vp8b200_mb);
     const size_t aux_b = ((size_t)n_aux * sizeof(vp8b200_aux) + 255) & ~(size_t)255;
     const size_t coef_b = (size_t)n_coef * 32;
     const size_t mb_pad = (mb_b + 255) & ~(size_t)255;
-    const bool key = hdr->frame_type == 0;
-    uint32_t *ilist = NULL;
-    unsigned n_intra = c->n_mb;
-    if (!key) {
-        ilist = (uint32_t *)malloc((size_t)c->n_mb * sizeof(uint32_t));
-        if (!ilist) { delete s; return VP8B200_ERR_NOMEM; }
-        n_intra = wavefront_order(c->geo, mb, c->n_mb, ilist, c->diag_tmp);
-    }
     const size_t coef_pad = (coef_b + 255) & ~(size_t)255;
     cudaError_t e = cudaMalloc((void **)&s->d_blob, mb_pad + aux_b + coef_pad + (size_t)n_intra * 4 + 256);
     if (e != cudaSuccess) {
@@ -552,7 +569,7 @@ extern "C" int vp8b200_stage_frame(vp8b200_ctx *c, const vp8b200_frame_hdr *hdr,
     s->d_aux = (vp8b200_aux *)(s->d_blob + mb_pad);
     s->d_coef = (int16_t *)(s->d_blob + mb_pad + aux_b);
     s->n_intra = n_intra;
-    s->n_split = key ? 0 : count_split(mb, c->n_mb);
+    s->n_split = n_split;
     s->d_ilist = key ? NULL : (uint32_t *)(s->d_blob + mb_pad + aux_b + coef_pad);
     if (!key && n_intra) {
         cudaError_t e2 = cudaMemcpy(s->d_ilist, ilist, (size_t)n_intra * 4, cudaMemcpyHostToDevice);
