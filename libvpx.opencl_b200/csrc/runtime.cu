@@ -11,7 +11,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <new>
 #include <vector>
 #include "vp8b200_internal.h"
@@ -125,12 +127,25 @@ extern "C" void *vp8b200_host_alloc(size_t bytes)
 }
 extern "C" void vp8b200_host_free(void *p) { if (p) cudaFreeHost(p); }
 
+/* Live contexts.  A batch member borrows an event owned by its leader (batch_ev = the
+ * leader's lead_ev[r]), so a leader that goes away first has to retire those references. */
+static std::mutex g_live_mu;
+static std::vector<vp8b200_ctx *> g_live;
+
 static void free_ctx(vp8b200_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->batch_pending) cudaEventSynchronize(c->batch_ev);   /* a batch on another leader's stream may still use us */
     if (c->stream) cudaStreamSynchronize(c->stream);
+    {
+        /* every batch this context led has finished now: members need not (and, once the
+         * events below are destroyed, must not) wait for them any more */
+        std::lock_guard<std::mutex> lk(g_live_mu);
+        g_live.erase(std::remove(g_live.begin(), g_live.end(), c), g_live.end());
+        for (vp8b200_ctx *m : g_live)
+            if (m->batch_leader == c) { m->batch_pending = false; m->batch_leader = NULL; m->batch_ev = NULL; }
+    }
     for (int i = 0; i < c->n_fb; i++) cudaFree(c->fb[i]);
     for (int i = 0; i < NSLOT; i++) {
         Slot &s = c->slot[i];
@@ -271,6 +286,10 @@ extern "C" int vp8b200_create(vp8b200_ctx **out, int device, int width, int heig
         fprintf(stderr, "vp8b200_create: %s\n", c->err);
         free_ctx(c);
         return st;
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_live_mu);
+        g_live.push_back(c);
     }
     *out = c;
     return VP8B200_OK;

@@ -187,3 +187,40 @@ def test_batch_then_individual_use_is_ordered(gpu_lib):
         _compare(ctxs[s].fetch(1), oras[s].fb(1), geo, "ordered batch stream %d" % s)
     for c in ctxs:
         c.close()
+
+
+def test_leader_destroyed_before_its_batch_members(gpu_lib):
+    """The members of a batch borrow an event of the leader (first context of the batch).
+    Destroying the leader right after the batch - no sync, members untouched so far - must
+    leave the members usable: their frames are complete and later calls do not wait on the
+    dead leader."""
+    n_streams, mb_cols, mb_rows = 4, 22, 18
+    w, h = mb_cols * 16, mb_rows * 16
+    geo = frames.Geometry(w, h)
+    rng = np.random.default_rng(321)
+    ctxs = [abi.Context(w, h, 4) for _ in range(n_streams)]
+    oras = [OracleDecoder(w, h, 4) for _ in range(n_streams)]
+    for c, o in zip(ctxs, oras):
+        for fb, buf in enumerate(randrec.random_buffers(rng, geo.frame_size, 4)):
+            c.upload(fb, buf)
+            o.fb(fb)[:] = buf
+    f0 = [randrec.random_frame(rng, mb_cols, mb_rows, fbs=(0, 1, 2, 3)) for _ in range(n_streams)]
+    staged = [ctxs[0].stage(fr) for fr in f0]            # the leader owns the staged frames too
+    abi.batch_run(ctxs, staged)
+    ctxs[0].close()                                       # waits for its own batch, retires the borrowed events
+    f1 = [randrec.random_frame(rng, mb_cols, mb_rows, p_intra=0.1, fbs=(1, 0, 0, 0)) for _ in range(n_streams)]
+    for s in range(1, n_streams):
+        oras[s].frame(f0[s])
+        _compare(ctxs[s].fetch(0), oras[s].fb(0), geo, "member %d after the leader is gone" % s)
+        ctxs[s].submit(f1[s])
+        oras[s].frame(f1[s])
+        _compare(ctxs[s].fetch(1), oras[s].fb(1), geo, "member %d next frame" % s)
+    # the surviving contexts can form a new batch with a new leader
+    f2 = [randrec.random_frame(rng, mb_cols, mb_rows, fbs=(2, 1, 0, 0)) for _ in range(n_streams)]
+    staged = [ctxs[1].stage(f2[s]) for s in range(1, n_streams)]
+    abi.batch_run(ctxs[1:], staged)
+    for s in range(1, n_streams):
+        oras[s].frame(f2[s])
+        _compare(ctxs[s].fetch(2), oras[s].fb(2), geo, "member %d in the second batch" % s)
+    for c in ctxs[1:]:
+        c.close()
