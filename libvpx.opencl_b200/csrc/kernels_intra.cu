@@ -35,7 +35,8 @@
 
 /* B_PRED predictor table: [mode][pixel] = i0 | i1<<4 | i2<<8 | kind<<12 over the edge array
  * E[0..3] = L3 L2 L1 L0, E[4] = top-left, E[5..12] = A0..A7.
- * kind 0: (E[i0] + 2 E[i1] + E[i2] + 2) >> 2 ; 1: (E[i0] + E[i1] + 1) >> 1 ; 2: DC ; 3: TM */
+ * kind 0: (E[i0] + 2 E[i1] + E[i2] + 2) >> 2 ; 1: (E[i0] + E[i1] + 1) >> 1 ; 2: DC ;
+ * 3: TM = clamp(E[i0] - E[i1] + E[i2]) with (i0, i1, i2) = (above, top-left, left) */
 __constant__ unsigned short c_bpred[10][16];
 
 static unsigned short ent(int kind, int a, int b, int c) { return (unsigned short)(a | (b << 4) | (c << 8) | (kind << 12)); }
@@ -49,7 +50,7 @@ void vp8b200_upload_intra_constants()
         for (int c = 0; c < 4; c++) {
             const int p = r * 4 + c;
             t[VP8B200_B_DC_PRED][p] = ent(2, 0, 0, 0);
-            t[VP8B200_B_TM_PRED][p] = ent(3, 0, 0, 0);
+            t[VP8B200_B_TM_PRED][p] = ent(3, 5 + c, 4, 3 - r);
             t[VP8B200_B_VE_PRED][p] = A3(4 + c, 5 + c, 6 + c);
             /* rows: (tl,L0,L1) (L0,L1,L2) (L1,L2,L3) (L2,L3,L3) with L_k = E[3-k] */
             t[VP8B200_B_HE_PRED][p] = r == 0 ? A3(4, 3, 2) : r == 1 ? A3(3, 2, 1) : r == 2 ? A3(2, 1, 0) : A3(1, 0, 0);
@@ -136,6 +137,9 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
     __shared__ __align__(16) uint8_t s_ct[INTRA_WARPS][2][9 * CS];
     __shared__ __align__(16) short s_res[INTRA_WARPS][16][16];
     __shared__ uint8_t s_modes[INTRA_WARPS][16];
+    /* B_PRED, per step and lane: .x = table entry | residual << 16, .y = tile offset of the
+     * lane's edge element | tile offset of its pixel << 16 (0xffff: lane idle in this step) */
+    __shared__ uint2 s_pre[INTRA_WARPS][10][32];
     __shared__ unsigned short s_bpred[160];              /* per-lane indexing: shared, not constant */
     for (int i = threadIdx.x; i < 160; i += blockDim.x) s_bpred[i] = (&c_bpred[0][0])[i];
     if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u) - ticket_base;
@@ -176,7 +180,33 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
     }
     if (bpred && lane < 16) s_modes[warp][lane] = reinterpret_cast<const uint8_t *>(job.aux + mb.u.aux)[lane];
     const int pix = lane & 15, pr = pix >> 2, pc = pix & 3, which = lane >> 4;
-
+    /* B_PRED runs its 16 sub-blocks as a 10-step anti-diagonal wavefront (block (br,bc) at step
+     * bc + 2*br needs left, above and above-right, decodframe.c:200-237), at most two blocks per
+     * step: lanes 0-15 are the pixels of the first, 16-31 of the second.  Everything a step
+     * needs that does not depend on pixels - the predictor table entry of (mode, pixel) and the
+     * residual - is gathered here, before the wait for the neighbours.  (The loops stay
+     * rolled: every warp runs this code once per macroblock, so unrolled straight-line code
+     * would be fetched from the instruction cache hierarchy with no reuse.) */
+    if (bpred) {
+        __syncwarp();
+        /* lane p of a block fetches element p of the block's edge array E[0..3] = L3..L0,
+         * E[4] = top-left, E[5..12] = above / above-right */
+        const int e = min(pix, 12);
+        const int e_off = e < 4 ? (3 - e) * YS - 1 : e - 5 - YS;
+#pragma unroll 1
+        for (int step = 0; step < 10; step++) {
+            const int br = (step > 3 ? (step - 2) >> 1 : 0) + which, bc = step - 2 * br;
+            const bool act = br <= 3 && bc >= 0 && bc <= 3;
+            const int blk = act ? br * 4 + bc : 0;
+            const int b_off = act ? br * 4 * YS + bc * 4 : 0;          /* block pixel (0,0) in the tile */
+            /* column 3 takes its above-right from row -1 of the MB (reconintra4x4.c:305-317) */
+            const int ld_off = (act && e >= 9 && bc == 3) ? -YS + 16 + e - 9 : b_off + e_off;
+            const int st_off = act ? b_off + pr * YS + pc : 0xffff;
+            s_pre[warp][step][lane] = make_uint2(
+                s_bpred[s_modes[warp][blk] * 16 + pix] | ((unsigned)(unsigned short)s_res[warp][blk][pix] << 16),
+                (unsigned)(ld_off & 0xffff) | ((unsigned)st_off << 16));
+        }
+    }
     uint8_t *YT = s_yt[warp] + YS + 16;                  /* tile pixel (0,0) */
     uint8_t *UT = s_ct[warp][0] + CS + 4, *VT = s_ct[warp][1] + CS + 4;
     uint8_t *const dy = job.dst + g.y_off + (size_t)mb_row * 16 * g.y_stride + mb_col * 16;
@@ -299,37 +329,33 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
         store4x4(YT + by * YS + bx, YS, px);
     }
     if (bpred) {
-        /* 16 sub-blocks, anti-diagonal wavefront: block (br,bc) at step bc + 2*br needs left,
-         * above and above-right (decodframe.c:200-237).  Two blocks per step at most: lanes
-         * 0-15 are the pixels of the first, 16-31 of the second. */
+        /* Per step one shared-memory load per lane - lane p of a block fetches element p of
+         * the block's edge array E[0..3] = L3..L0, E[4] = top-left, E[5..12] = above /
+         * above-right (column 3 takes its above-right from row -1 of the MB,
+         * reconintra4x4.c:305-317) - then the three taps of the lane's pixel come from the
+         * other lanes by shuffle.  No divergent code on the dependency chain. */
         __syncwarp();
+        const bool e_dc = pix < 4 || (pix >= 5 && pix < 9);
+        const int half = lane & 16;
 #pragma unroll 1
         for (int step = 0; step < 10; step++) {
-            /* blocks on this anti-diagonal: br from max(0,(step-3+1)/2) .. min(3, step/2) */
-            const int br_lo = step > 3 ? (step - 2) >> 1 : 0;
-            const int br = br_lo + which, bc = step - 2 * br;
-            const bool act = br <= 3 && bc >= 0 && bc <= 3 && br <= (step >> 1);
-            if (act) {
-                const int blk = br * 4 + bc;
-                const int mode = s_modes[warp][blk];
-                uint8_t *B = YT + br * 4 * YS + bc * 4;              /* block pixel (0,0) */
-                /* edge array element e: 0..3 = L3..L0, 4 = top-left, 5..12 = above / above-right;
-                 * column 3 takes its above-right from row -1 of the MB (reconintra4x4.c:305-317) */
-                auto E = [&](int e) -> int {
-                    if (e < 4) return B[(3 - e) * YS - 1];
-                    if (e < 9) return B[-YS + e - 5];
-                    return bc == 3 ? YT[-YS + 16 + e - 9] : B[-YS + e - 5];
-                };
-                const unsigned ent = s_bpred[mode * 16 + pix];
-                const int kind = ent >> 12;
-                int v;
-                if (kind == 0) v = (E(ent & 15) + 2 * E((ent >> 4) & 15) + E((ent >> 8) & 15) + 2) >> 2;
-                else if (kind == 1) v = (E(ent & 15) + E((ent >> 4) & 15) + 1) >> 1;
-                else if (kind == 2) v = (E(5) + E(6) + E(7) + E(8) + E(0) + E(1) + E(2) + E(3) + 4) >> 3;
-                else v = clamp255(E(5 + pc) - E(4) + E(3 - pr));
-                v = clamp255(v + s_res[warp][blk][pix]);
-                B[pr * YS + pc] = (uint8_t)v;
+            const uint2 t = s_pre[warp][step][lane];
+            const int edge = YT[(short)(t.y & 0xffff)];
+            const int ea = __shfl_sync(FULL_MASK, edge, half + (t.x & 15));
+            const int eb = __shfl_sync(FULL_MASK, edge, half + ((t.x >> 4) & 15));
+            const int ec = __shfl_sync(FULL_MASK, edge, half + ((t.x >> 8) & 15));
+            const int kind = (t.x >> 12) & 3;
+            int v = kind == 0 ? (ea + 2 * eb + ec + 2) >> 2 : (kind == 1 ? (ea + eb + 1) >> 1 : clamp255(ea - eb + ec));
+            if (__any_sync(FULL_MASK, kind == 2)) {                  /* B_DC_PRED: mean of L0..L3, A0..A3 */
+                int sum = e_dc ? edge : 0;
+                sum += __shfl_xor_sync(FULL_MASK, sum, 1);
+                sum += __shfl_xor_sync(FULL_MASK, sum, 2);
+                sum += __shfl_xor_sync(FULL_MASK, sum, 4);
+                sum += __shfl_xor_sync(FULL_MASK, sum, 8);
+                if (kind == 2) v = (sum + 4) >> 3;
             }
+            v = clamp255(v + (short)(t.x >> 16));
+            if ((t.y >> 16) != 0xffff) YT[t.y >> 16] = (uint8_t)v;
             __syncwarp();
         }
         /* the finished 16x16 goes out row by row */
