@@ -26,6 +26,9 @@
 #include "vp8b200_dev.cuh"
 
 #define INTRA_WARPS 4
+#ifndef INTRA_MIN_CTAS
+#define INTRA_MIN_CTAS 8          /* caps the kernel at 64 registers */
+#endif
 #ifndef INTRA_SPIN
 #define INTRA_SPIN 0
 #define INTRA_SLEEP 32
@@ -127,7 +130,7 @@ __device__ __forceinline__ void block_mode(int mode, const uint8_t *T, int ts, i
     }
 }
 
-__global__ void __launch_bounds__(INTRA_WARPS * 32)
+__global__ void __launch_bounds__(INTRA_WARPS * 32, INTRA_MIN_CTAS)
 k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const unsigned max_intra,
         unsigned *ticket, const unsigned ticket_base)
 {
@@ -221,11 +224,21 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
      * producer's frame stores are off the dependency chain.  Inter neighbours were finished by
      * k_inter and are read from the frame; frame edges are synthesised (setupintrarecon.c:15-32,
      * extend.c:160-185).  Lanes 0-7 left column words, 8-15 above row words, 16-18 the top-left
-     * pixels of Y/U/V, 19 the above-right luma word. ---- */
-    {
-        const unsigned long long *msg = job.intra_msg;
+     * pixels of Y/U/V, 19 the above-right luma word.
+     *
+     * The macroblock is done in two phases, luma then chroma, each: fetch that plane's
+     * borders, predict + add the residual, export that plane's words.  The right-hand
+     * neighbour's luma (the long part: the B_PRED wavefront) needs only the luma words, so
+     * the chroma work of this macroblock overlaps with the neighbour's luma instead of
+     * sitting on the dependency chain.  The code of a phase exists once (rolled loop: every
+     * warp runs it once per macroblock, straight-line copies would only miss in the
+     * instruction cache). ---- */
+    const unsigned long long *msg = job.intra_msg;
+    const bool luma_lane = lane < 4 || (lane >= 8 && lane < 12) || lane == 16 || lane == 19;
+#pragma unroll 1
+    for (int phase = 0; phase < 2; phase++) {
         unsigned w = 0;
-        if (lane < 20) {
+        if (lane < 20 && luma_lane == (phase == 0)) {
             /* which neighbour this lane reads, which word of its export, or which frame bytes */
             const int grp = lane < 8 ? 0 : (lane < 16 ? 1 : (lane < 19 ? 2 : 3));   /* left, above, above-left, above-right */
             const bool exists = grp == 0 ? left : (up && (grp == 2 ? left : (grp == 3 ? right : true)));
@@ -267,119 +280,120 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
                 }
             }
         }
-        /* above-right of the last MB column: replicate the last pixel of the above row */
-        const unsigned w11 = __shfl_sync(FULL_MASK, w, 11);
-        if (lane == 19 && up && !right) w = (w11 >> 24) * 0x01010101u;
+        if (phase == 0) {
+            /* above-right of the last MB column: replicate the last pixel of the above row */
+            const unsigned w11 = __shfl_sync(FULL_MASK, w, 11);
+            if (lane == 19 && up && !right) w = (w11 >> 24) * 0x01010101u;
+        }
         /* scatter into the tiles */
-        if (lane < 4) {
+        if (lane < 20 && luma_lane == (phase == 0)) {
+            if (lane < 4) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) YT[(4 * lane + i) * YS - 1] = (uint8_t)(w >> (8 * i));
-        } else if (lane < 8) {
-            uint8_t *CT = lane < 6 ? UT : VT;
+                for (int i = 0; i < 4; i++) YT[(4 * lane + i) * YS - 1] = (uint8_t)(w >> (8 * i));
+            } else if (lane < 8) {
+                uint8_t *CT = lane < 6 ? UT : VT;
 #pragma unroll
-            for (int i = 0; i < 4; i++) CT[(4 * (lane & 1) + i) * CS - 1] = (uint8_t)(w >> (8 * i));
-        } else if (lane < 12) {
-            *reinterpret_cast<unsigned *>(YT - YS + 4 * (lane - 8)) = w;
-        } else if (lane < 16) {
-            *reinterpret_cast<unsigned *>((lane < 14 ? UT : VT) - CS + 4 * (lane & 1)) = w;
-        } else if (lane < 19) {
-            uint8_t *T = lane == 16 ? YT : (lane == 17 ? UT : VT);
-            T[-(lane == 16 ? YS : CS) - 1] = (uint8_t)(w >> 24);
-        } else if (lane == 19) {
-            *reinterpret_cast<unsigned *>(YT - YS + 16) = w;
-        }
-    }
-    __syncwarp();
-    int a_px, l_px;
-    /* ---- DC values (reconintra.c:167-195, :434-462): lanes 0-15 sum luma, 16-23 U, 24-31 V ---- */
-    int dc;
-    {
-        const uint8_t *T = lane < 16 ? YT : (lane < 24 ? UT : VT);
-        const int ts = lane < 16 ? YS : CS, i = lane < 16 ? lane : (lane & 7);
-        a_px = up ? T[-ts + i] : 0;
-        l_px = left ? T[i * ts - 1] : 0;
-        int s = a_px + l_px;
-        /* segmented sums: 16 lanes, 8 lanes, 8 lanes */
-        s += __shfl_xor_sync(FULL_MASK, s, 1);
-        s += __shfl_xor_sync(FULL_MASK, s, 2);
-        s += __shfl_xor_sync(FULL_MASK, s, 4);
-        const int s8 = s;
-        s += __shfl_xor_sync(FULL_MASK, s, 8);
-        const int sum = lane < 16 ? s : s8;
-        const int lg = lane < 16 ? 3 : 2;
-        const int shift = lg + (up ? 1 : 0) + (left ? 1 : 0);
-        dc = (up || left) ? (sum + (1 << (shift - 1))) >> shift : 128;
-    }
-    const int dc_y = __shfl_sync(FULL_MASK, dc, 0), dc_u = __shfl_sync(FULL_MASK, dc, 16), dc_v = __shfl_sync(FULL_MASK, dc, 24);
-
-    /* ---- chroma (lanes 16..23) and whole-block luma (lanes 0..15), lane = 4x4 block ---- */
-    if (lane >= 16 && lane < 24) {
-        const int j = lane & 3, bx = (j & 1) * 4, by = (j >> 1) * 4;
-        unsigned px[4];
-        block_mode(mb.uv_mode, lane < 20 ? UT : VT, CS, bx, by, lane < 20 ? dc_u : dc_v, px);
-        if (has_res) add_res(px, res);
-        store4x4((lane < 20 ? du : dv) + by * g.uv_stride + bx, g.uv_stride, px);
-        store4x4((lane < 20 ? UT : VT) + by * CS + bx, CS, px);       /* for the export below */
-    } else if (lane < 16 && !bpred) {
-        const int bx = (lane & 3) * 4, by = (lane >> 2) * 4;
-        unsigned px[4];
-        block_mode(mb.y_mode, YT, YS, bx, by, dc_y, px);
-        if (has_res) add_res(px, res);
-        store4x4(dy + by * g.y_stride + bx, g.y_stride, px);
-        store4x4(YT + by * YS + bx, YS, px);
-    }
-    if (bpred) {
-        /* Per step one shared-memory load per lane - lane p of a block fetches element p of
-         * the block's edge array E[0..3] = L3..L0, E[4] = top-left, E[5..12] = above /
-         * above-right (column 3 takes its above-right from row -1 of the MB,
-         * reconintra4x4.c:305-317) - then the three taps of the lane's pixel come from the
-         * other lanes by shuffle.  No divergent code on the dependency chain. */
-        __syncwarp();
-        const bool e_dc = pix < 4 || (pix >= 5 && pix < 9);
-        const int half = lane & 16;
-#pragma unroll 1
-        for (int step = 0; step < 10; step++) {
-            const uint2 t = s_pre[warp][step][lane];
-            const int edge = YT[(short)(t.y & 0xffff)];
-            const int ea = __shfl_sync(FULL_MASK, edge, half + (t.x & 15));
-            const int eb = __shfl_sync(FULL_MASK, edge, half + ((t.x >> 4) & 15));
-            const int ec = __shfl_sync(FULL_MASK, edge, half + ((t.x >> 8) & 15));
-            const int kind = (t.x >> 12) & 3;
-            int v = kind == 0 ? (ea + 2 * eb + ec + 2) >> 2 : (kind == 1 ? (ea + eb + 1) >> 1 : clamp255(ea - eb + ec));
-            if (__any_sync(FULL_MASK, kind == 2)) {                  /* B_DC_PRED: mean of L0..L3, A0..A3 */
-                int sum = e_dc ? edge : 0;
-                sum += __shfl_xor_sync(FULL_MASK, sum, 1);
-                sum += __shfl_xor_sync(FULL_MASK, sum, 2);
-                sum += __shfl_xor_sync(FULL_MASK, sum, 4);
-                sum += __shfl_xor_sync(FULL_MASK, sum, 8);
-                if (kind == 2) v = (sum + 4) >> 3;
+                for (int i = 0; i < 4; i++) CT[(4 * (lane & 1) + i) * CS - 1] = (uint8_t)(w >> (8 * i));
+            } else if (lane < 12) {
+                *reinterpret_cast<unsigned *>(YT - YS + 4 * (lane - 8)) = w;
+            } else if (lane < 16) {
+                *reinterpret_cast<unsigned *>((lane < 14 ? UT : VT) - CS + 4 * (lane & 1)) = w;
+            } else if (lane < 19) {
+                uint8_t *T = lane == 16 ? YT : (lane == 17 ? UT : VT);
+                T[-(lane == 16 ? YS : CS) - 1] = (uint8_t)(w >> 24);
+            } else {
+                *reinterpret_cast<unsigned *>(YT - YS + 16) = w;
             }
-            v = clamp255(v + (short)(t.x >> 16));
-            if ((t.y >> 16) != 0xffff) YT[t.y >> 16] = (uint8_t)v;
-            __syncwarp();
         }
-        /* the finished 16x16 goes out row by row */
-        if (lane < 16) {
+        __syncwarp();
+        /* ---- DC value (reconintra.c:167-195, :434-462) when this phase's mode is DC_PRED:
+         * lanes 0-15 sum luma, 16-23 U, 24-31 V ---- */
+        int dc = 128;
+        if ((phase == 0 ? (!bpred && mb.y_mode == VP8B200_DC_PRED) : mb.uv_mode == VP8B200_DC_PRED) && (up || left)) {
+            const uint8_t *T = lane < 16 ? YT : (lane < 24 ? UT : VT);
+            const int ts = lane < 16 ? YS : CS, i = lane < 16 ? lane : (lane & 7);
+            int sum = (up ? T[-ts + i] : 0) + (left ? T[i * ts - 1] : 0);
+            /* segmented sums: 16 lanes, 8 lanes, 8 lanes */
+            sum += __shfl_xor_sync(FULL_MASK, sum, 1);
+            sum += __shfl_xor_sync(FULL_MASK, sum, 2);
+            sum += __shfl_xor_sync(FULL_MASK, sum, 4);
+            if (lane < 16) sum += __shfl_xor_sync(0xffffu, sum, 8);
+            const int shift = (lane < 16 ? 3 : 2) + (up ? 1 : 0) + (left ? 1 : 0);
+            dc = (sum + (1 << (shift - 1))) >> shift;
+            /* the V sum sits in lanes 24-31, the V blocks are predicted by lanes 20-23 */
+            const int dc_v = __shfl_sync(FULL_MASK, dc, 24);
+            if (lane >= 20) dc = dc_v;
+        }
+        if (phase == 0) {
+            if (!bpred) {
+                /* whole-block luma modes, lane = 4x4 block */
+                if (lane < 16) {
+                    const int bx = (lane & 3) * 4, by = (lane >> 2) * 4;
+                    unsigned px[4];
+                    block_mode(mb.y_mode, YT, YS, bx, by, dc, px);
+                    if (has_res) add_res(px, res);
+                    store4x4(dy + by * g.y_stride + bx, g.y_stride, px);
+                    store4x4(YT + by * YS + bx, YS, px);              /* for the export below */
+                }
+            } else {
+                /* Per step one shared-memory load per lane - lane p of a block fetches element p
+                 * of the block's edge array - then the three taps of the lane's pixel come from
+                 * the other lanes by shuffle.  No divergent code on the dependency chain. */
+                const bool e_dc = pix < 4 || (pix >= 5 && pix < 9);
+                const int half = lane & 16;
+#pragma unroll 1
+                for (int step = 0; step < 10; step++) {
+                    const uint2 t = s_pre[warp][step][lane];
+                    const int edge = YT[(short)(t.y & 0xffff)];
+                    const int ea = __shfl_sync(FULL_MASK, edge, half + (t.x & 15));
+                    const int eb = __shfl_sync(FULL_MASK, edge, half + ((t.x >> 4) & 15));
+                    const int ec = __shfl_sync(FULL_MASK, edge, half + ((t.x >> 8) & 15));
+                    const int kind = (t.x >> 12) & 3;
+                    int v = kind == 0 ? (ea + 2 * eb + ec + 2) >> 2 : (kind == 1 ? (ea + eb + 1) >> 1 : clamp255(ea - eb + ec));
+                    if (__any_sync(FULL_MASK, kind == 2)) {          /* B_DC_PRED: mean of L0..L3, A0..A3 */
+                        int sum = e_dc ? edge : 0;
+                        sum += __shfl_xor_sync(FULL_MASK, sum, 1);
+                        sum += __shfl_xor_sync(FULL_MASK, sum, 2);
+                        sum += __shfl_xor_sync(FULL_MASK, sum, 4);
+                        sum += __shfl_xor_sync(FULL_MASK, sum, 8);
+                        if (kind == 2) v = (sum + 4) >> 3;
+                    }
+                    v = clamp255(v + (short)(t.x >> 16));
+                    if ((t.y >> 16) != 0xffff) YT[t.y >> 16] = (uint8_t)v;
+                    __syncwarp();
+                }
+            }
+        } else if (lane >= 16 && lane < 24) {
+            /* chroma, lane = 4x4 block */
+            const int j = lane & 3, bx = (j & 1) * 4, by = (j >> 1) * 4;
+            unsigned px[4];
+            block_mode(mb.uv_mode, lane < 20 ? UT : VT, CS, bx, by, dc, px);
+            if (has_res) add_res(px, res);
+            store4x4((lane < 20 ? du : dv) + by * g.uv_stride + bx, g.uv_stride, px);
+            store4x4((lane < 20 ? UT : VT) + by * CS + bx, CS, px);   /* for the export below */
+        }
+        /* ---- export this plane's bottom row + right column for the neighbours still to come ---- */
+        __syncwarp();
+        if (lane < 16 && ((lane & 4) != 0) == (phase == 1)) {
+            unsigned x;
+            if (lane < 4) x = *reinterpret_cast<const unsigned *>(YT + 15 * YS + 4 * lane);
+            else if (lane < 8) x = *reinterpret_cast<const unsigned *>((lane < 6 ? UT : VT) + 7 * CS + 4 * (lane & 1));
+            else if (lane < 12) {
+                const uint8_t *q = YT + (4 * (lane - 8)) * YS + 15;
+                x = q[0] | (q[YS] << 8) | (q[2 * YS] << 16) | ((unsigned)q[3 * YS] << 24);
+            } else {
+                const uint8_t *q = (lane < 14 ? UT : VT) + (4 * (lane & 1)) * CS + 7;
+                x = q[0] | (q[CS] << 8) | (q[2 * CS] << 16) | ((unsigned)q[3 * CS] << 24);
+            }
+            const unsigned long long v = ((unsigned long long)epoch << 32) | x;
+            unsigned long long *p = job.intra_msg + (size_t)mbi * 16 + lane;
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+        }
+        /* the finished B_PRED 16x16 goes out row by row, after the hand-off */
+        if (phase == 0 && bpred && lane < 16) {
             const unsigned *r = reinterpret_cast<const unsigned *>(YT + lane * YS);
             *reinterpret_cast<uint4 *>(dy + lane * g.y_stride) = make_uint4(r[0], r[1], r[2], r[3]);
         }
-    }
-    /* ---- export bottom row + right column for the neighbours still to come ---- */
-    __syncwarp();
-    if (lane < 16) {
-        unsigned w;
-        if (lane < 4) w = *reinterpret_cast<const unsigned *>(YT + 15 * YS + 4 * lane);
-        else if (lane < 8) w = *reinterpret_cast<const unsigned *>((lane < 6 ? UT : VT) + 7 * CS + 4 * (lane & 1));
-        else if (lane < 12) {
-            const uint8_t *q = YT + (4 * (lane - 8)) * YS + 15;
-            w = q[0] | (q[YS] << 8) | (q[2 * YS] << 16) | ((unsigned)q[3 * YS] << 24);
-        } else {
-            const uint8_t *q = (lane < 14 ? UT : VT) + (4 * (lane & 1)) * CS + 7;
-            w = q[0] | (q[CS] << 8) | (q[2 * CS] << 16) | ((unsigned)q[3 * CS] << 24);
-        }
-        const unsigned long long v = ((unsigned long long)epoch << 32) | w;
-        unsigned long long *p = job.intra_msg + (size_t)mbi * 16 + lane;
-        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
     }
 }
 
