@@ -176,12 +176,22 @@ def run_b200(args):
     g_sa = [[(C.c_void_p * len(gstaged[f][gi]))(*gstaged[f][gi]) for gi in range(G)] for f in range(F)]
     g_n = [len(gc) for gc in gctx]
 
-    def step(i):
-        f = i % F
+    # independent streams are not in phase: group gi runs off[gi] frames ahead of group 0, so one
+    # group's key frame (a latency-bound intra wavefront) overlaps the other groups' P frames
+    off = [(gi * F) // G if args.stagger else 0 for gi in range(G)]
+
+    def run_group(gi, f):
+        st = L.vp8b200_batch_run(g_ca[gi], g_sa[f][gi], g_n[gi])
+        if st:
+            raise SystemExit("bench: vp8b200_batch_run failed: %d" % st)
+
+    def step(i, staggered=True):
         for gi in range(G):
-            st = L.vp8b200_batch_run(g_ca[gi], g_sa[f][gi], g_n[gi])
-            if st:
-                raise SystemExit("bench: vp8b200_batch_run failed: %d" % st)
+            run_group(gi, (i + (off[gi] if staggered else 0)) % F)
+
+    for gi in range(G):                          # pre-roll (untimed): bring every group to its phase
+        for f in range(off[gi]):
+            run_group(gi, f)
 
     def sync_all():
         for gc in gctx:
@@ -225,7 +235,7 @@ def run_b200(args):
     checked = 0
     check_streams = list(range(0, S, max(1, S // 4)))[:4]
     for f in range(0 if not args.skip_verify else F, F):
-        step(f)
+        step(f, staggered=False)                 # every clip restarts at its key frame
         for s in check_streams:
             fr = recs[mine[s]].frames[f]
             if fr.show_frame:
@@ -279,6 +289,7 @@ def run_b200(args):
             "warmup": W, "ms_per_step": round(tot_s * 1e3 / K, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": "c5_64x1080p", "streams_per_gpu": S, "frames_per_clip": F, "stream_groups": G,
+                       "group_phase_offsets_frames": off,
                        "unique_clips": len(clips), "resolution": "1920x1080 (coded 1920x1088)",
                        "profile": 0, "loop_filter": "normal", "mc": "sixtap",
                        "step": "one frame of each of the %d streams (one batched launch per kernel and stream group)" % S,
@@ -369,6 +380,8 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=64, help="independent streams per GPU")
     ap.add_argument("--groups", type=int, default=4, help="stream groups batched on separate CUDA streams")
+    ap.add_argument("--stagger", type=int, default=1,
+                    help="1: stream group g plays g*F/G frames ahead (streams out of phase); 0: all streams on the same frame")
     ap.add_argument("--e2e-threads", type=int, default=0)
     ap.add_argument("--e2e-repeat", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -29,7 +29,10 @@
 #ifndef LF_ROWS_PER_CTA
 #define LF_ROWS_PER_CTA 4
 #endif
+#ifndef LF_RING
 #define LF_RING 4                 /* shared-memory message slots per row (power of two) */
+#endif
+static_assert(1 + (LF_ROWS_PER_CTA - 1) * LF_RING <= 16, "one named barrier per (row pair, ring slot)");
 #ifndef LF_PF
 #define LF_PF 2                   /* prefetch distance in macroblocks (1: 0.80 ms, 2: 0.72, 3: 0.77, 5: 0.88) */
 #endif
@@ -114,6 +117,19 @@ __device__ __forceinline__ void edge8(int &p3, int &p2, int &p1, int &p0, int &q
     else if (MB) lf_mbedge(p3, p2, p1, p0, q0, q1, q2, q3, P);
     else lf_inner(p3, p2, p1, p0, q0, q1, q2, q3, P);
 }
+
+/* ---- in-CTA hand-off: named barriers ---------------------------------------------------
+ * Producer row w and consumer row w+1 meet on barrier 1 + w*LF_RING + (col % LF_RING): the
+ * producer stores the ring slot and ARRIVES (does not wait), the consumer SYNCs.  A waiting
+ * consumer is suspended by the hardware and issues nothing, where a shared-memory spin took
+ * half of the kernel's issue slots (profiles/r01_summary_v8.md).  A barrier id is reused
+ * every LF_RING columns; the ring-full check keeps the producer from arriving at a barrier
+ * whose previous phase the consumer has not left. */
+#ifndef LF_BAR
+#define LF_BAR 1
+#endif
+__device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void bar_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
 /* ---- global hand-off (across CTAs) ------------------------------------------------------ */
 __device__ __forceinline__ void st_msg2(uint8_t *p, unsigned a, unsigned b, unsigned tag)
@@ -253,9 +269,13 @@ k_loopfilter(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g,
                 if (luma) *reinterpret_cast<uint4 *>(slot) = make_uint4(m[0], m[1], m[2], m[3]);
                 else *reinterpret_cast<uint2 *>(slot) = make_uint2(m[0], m[1]);
             }
+#if LF_BAR
+            bar_arrive(1 + warp * LF_RING + (col & (LF_RING - 1)));
+#else
             __threadfence_block();
             __syncwarp();
             if (lane == 0) s_sent[warp] = (unsigned)col + 1;
+#endif
         } else if (sender) {
             g_send(gmsg_out + (size_t)col * 256, m, tag, luma);
         }
@@ -322,8 +342,12 @@ k_loopfilter(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g,
         /* ---- the 4 rows above arrive as a message from the row above ---- */
         if (top) {
             if (recv_smem) {
+#if LF_BAR
+                bar_wait(1 + (warp - 1) * LF_RING + (c & (LF_RING - 1)));
+#else
                 for (int tries = 0; s_sent[warp - 1] <= (unsigned)c; tries++) if (tries > 24) __nanosleep(64);   /* spin briefly, then back off */
                 __threadfence_block();
+#endif
                 if (receiver) {
                     const uint8_t *slot = s_ring[warp - 1][c & (LF_RING - 1)] + sr_off;
                     if (luma) *reinterpret_cast<uint4 *>(tile + pi * 16) = *reinterpret_cast<const uint4 *>(slot);
