@@ -10,7 +10,9 @@
  * c once row r-1 has done the left edge of column c+1.  There are no flags and no fences on
  * that path: a row hands the bottom 4 pixel rows of each finished macroblock DOWN as a
  * message and the row below finishes (top-edge filter) and stores the 3 rows it modifies.
- *   - rows in the same CTA: message through a shared-memory ring (LF_RING slots per row);
+ *   - rows in the same CTA: message through a shared-memory ring (LF_RING slots per row),
+ *     producer and consumer meeting on a named barrier per ring slot (bar.arrive / bar.sync:
+ *     a waiting row is suspended by the hardware and issues nothing);
  *   - across CTAs: tagged 64-bit words in global memory, {32 bits of pixels, 32-bit frame
  *     tag}; an aligned 64-bit access is single-copy atomic, so a word whose tag matches
  *     carries valid pixels and the consumer simply polls the words (NCCL's LL idea).
@@ -19,10 +21,16 @@
  * (lanes 0-15 luma rows, 16-23 U rows, 24-31 V rows; rows live in registers, the 4 pixels
  * left of the MB are carried over from the previous column), transposes through a 512-byte
  * shared-memory tile, filters the horizontal edges with lane = pixel column, and transposes
- * back.  The last 4 columns of a macroblock are stored one iteration later, after the next
- * macroblock's left-edge filter has modified them.  Filters are branch-free (select on the
- * mask) so that a lane's instruction stream is short and free of divergence; macroblocks
+ * back.  A macroblock is stored one iteration later, after the next macroblock's left-edge
+ * filter has modified its last 3 columns: one 16-byte (luma) / 8-byte (chroma) store per pixel
+ * row.  Filters are branch-free (select on the mask) and chroma lanes run the two luma-only
+ * inner edges on scratch data, so the normal filter has no divergent branch; macroblocks
  * without inner edges (skip_lf) only move the 8 rows the top edge needs through the tile.
+ *
+ * Memory: pixel rows arrive through a lane-private cp.async ring LF_PF macroblocks deep (the
+ * row latency under a 64-stream load is several iterations), record words are read 32
+ * macroblocks at a time one batch ahead and turned into filter limits off the chain
+ * (measurements: profiles/r01_summary_v8.md).
  */
 #include "vp8b200_dev.cuh"
 
@@ -34,7 +42,7 @@
 #endif
 static_assert(1 + (LF_ROWS_PER_CTA - 1) * LF_RING <= 16, "one named barrier per (row pair, ring slot)");
 #ifndef LF_PF
-#define LF_PF 2                   /* prefetch distance in macroblocks (1: 0.80 ms, 2: 0.72, 3: 0.77, 5: 0.88) */
+#define LF_PF 8                   /* cp.async prefetch distance in macroblocks (power of two, >= 2; 2: 1.1 ms, 4: 0.61, 8: 0.50, 16: 0.50 per 64x1080p) */
 #endif
 
 __device__ __forceinline__ int sc(int v) { return max(min(v, 127), -128); }
@@ -109,11 +117,11 @@ __device__ __forceinline__ unsigned pack(int a, int b, int c, int d)
     return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
 }
 
-template <bool MB>
+template <bool MB, bool SIMPLE>
 __device__ __forceinline__ void edge8(int &p3, int &p2, int &p1, int &p0, int &q0, int &q1, int &q2, int &q3,
-                                      bool simple, const LfParams &P)
+                                      const LfParams &P)
 {
-    if (simple) lf_simple(p1, p0, q0, q1, MB ? P.mblim : P.blim);
+    if (SIMPLE) lf_simple(p1, p0, q0, q1, MB ? P.mblim : P.blim);
     else if (MB) lf_mbedge(p3, p2, p1, p0, q0, q1, q2, q3, P);
     else lf_inner(p3, p2, p1, p0, q0, q1, q2, q3, P);
 }
@@ -127,6 +135,21 @@ __device__ __forceinline__ void edge8(int &p3, int &p2, int &p1, int &p0, int &q
  * whose previous phase the consumer has not left. */
 #ifndef LF_BAR
 #define LF_BAR 1
+#endif
+#ifndef LF_MIN_CTAS
+#define LF_MIN_CTAS 4
+#endif
+#ifndef LF_EARLY
+#define LF_EARLY 0                /* 1: hand the previous MB down right after the left-edge filter (measured slower under load) */
+#endif
+#ifndef LF_POLL_SLEEP
+#define LF_POLL_SLEEP 100         /* ns between polls of a global message after 8 immediate tries */
+#endif
+#ifndef LF_START_SLEEP
+#define LF_START_SLEEP 0          /* ns per row group slept before the first poll (at most half the real lag) */
+#endif
+#ifndef LF_NODIV
+#define LF_NODIV 1                /* chroma lanes run the luma-only edges on scratch data instead of diverging */
 #endif
 __device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void bar_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
@@ -157,24 +180,327 @@ __device__ __forceinline__ void g_recv(const uint8_t *slot, unsigned (&m)[4], un
         bool ok = (unsigned)(a >> 32) == tag && (unsigned)(b >> 32) == tag;
         if (luma) ok = ok && (unsigned)(c >> 32) == tag && (unsigned)(d >> 32) == tag;
         if (ok) break;
-        if (++tries > 8) __nanosleep(100);
+        if (++tries > 8) __nanosleep(LF_POLL_SLEEP);
     }
     m[0] = (unsigned)a; m[1] = (unsigned)b; m[2] = (unsigned)c; m[3] = (unsigned)d;
 }
 
-__global__ void __launch_bounds__(LF_ROWS_PER_CTA * 32, 32 / LF_ROWS_PER_CTA)
+#ifdef LF_TRACE
+#include <cstdio>
+#define TR_DECL long long tr_[6] = {0, 0, 0, 0, 0, 0}, tr_t = clock64(), tr_start = tr_t
+#define TR(i) do { long long n_ = clock64(); tr_[i] += n_ - tr_t; tr_t = n_; } while (0)
+#else
+#define TR_DECL
+#define TR(i)
+#endif
+
+/* mode_lf_lut, loopfilter.c:52-63, two bits per y_mode: DC,V,H,TM,ZEROMV -> 1 ; B_PRED -> 0 ;
+ * NEARESTMV,NEARMV,NEWMV -> 2 ; SPLITMV -> 3 */
+#define LF_MODE_CLASS_LUT (1u | 1u << 2 | 1u << 4 | 1u << 6 | 0u << 8 | 2u << 10 | 2u << 12 | 1u << 14 | 2u << 16 | 3u << 18)
+
+/* one macroblock row, left to right (see the header comment) */
+template <bool SIMPLE>
+__device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const int mb_row, const int warp, const int lane,
+                                       const unsigned *s_par, uint8_t *s_tile_w, uint8_t *s_scratch_w, uint8_t *s_pf_w,
+                                       uint8_t (*s_ring)[LF_RING][128], volatile unsigned *s_rcvd)
+{
+    const unsigned tag = job.epoch_lf;                     /* marks this frame's global messages */
+
+    /* lane geometry */
+    const bool luma = lane < 16;
+    const int pi = luma ? lane : (lane & 7);               /* row (V phase) / column (H phase) */
+    const int stride = luma ? g.y_stride : g.uv_stride;
+    const int mbw = luma ? 16 : 8;                         /* MB width = height in this plane */
+    uint8_t *plane = job.dst + (luma ? g.y_off : (lane < 24 ? g.u_off : g.v_off));
+    uint8_t *rowp = plane + (size_t)(mb_row * mbw + pi) * stride;      /* my pixel row, x = 0 */
+    const bool lane_on = luma || !SIMPLE;                  /* simple filter: luma only */
+    uint8_t *tile = s_tile_w + (luma ? 0 : (lane < 24 ? 320 : 416));
+    /* tile rows 12.. exist for luma only; chroma lanes run the same (branch-free) code on a
+     * scratch area instead of diverging */
+    uint8_t *tile_hi = luma ? tile : s_scratch_w + (lane < 24 ? 0 : 192);
+    const bool top = mb_row > 0;
+    const bool last_row = mb_row == g.mb_rows - 1;
+    /* rows >= keep of every MB (not in the last MB row) are finished and stored by the row
+     * below; this row hands rows keep.. down as a message instead */
+    const int keep = luma ? 12 : 4;
+    const bool owns_store = lane_on && (last_row || pi <= keep);
+    const bool sender = lane_on && !last_row && pi >= keep;
+    const bool receiver = lane_on && top && pi < 4;
+    const bool send_smem = warp < LF_ROWS_PER_CTA - 1;     /* consumer row lives in this CTA */
+    const bool recv_smem = warp > 0;
+    /* global slot offsets */
+    const int gs_off = luma ? (pi - 12) * 32 : (lane < 24 ? 128 : 192) + (pi - 4) * 16;
+    const int gr_off = luma ? pi * 32 : (lane < 24 ? 128 : 192) + pi * 16;
+    uint8_t *gmsg_out = job.lf_msg + (size_t)mb_row * g.mb_cols * 256 + gs_off;
+    const uint8_t *gmsg_in = job.lf_msg + (size_t)(mb_row - 1) * g.mb_cols * 256 + gr_off;
+    /* shared ring offsets */
+    const int ss_off = luma ? (pi - 12) * 16 : (lane < 24 ? 64 : 96) + (pi - 4) * 8;
+    const int sr_off = luma ? pi * 16 : (lane < 24 ? 64 : 96) + pi * 8;
+
+    const unsigned *mbrec = reinterpret_cast<const unsigned *>(job.mb + (size_t)mb_row * g.mb_cols);
+    /* Per-MB decisions (loopfilter.c:245-253), 32 macroblocks at a time: lane l loads the first
+     * record word of macroblock batch + l one batch ahead and turns it into the parameter word
+     * (level -> limits through s_par, bit 31 = no inner edges); the loop broadcasts one word per
+     * macroblock by shuffle, so neither the record load nor the level arithmetic sits on the
+     * per-macroblock dependency chain. */
+    auto par_of = [&](unsigned rec) -> unsigned {
+        const int y_mode = rec & 255, ref = (rec >> 16) & 255, flags = rec >> 24;
+        const int mclass = (LF_MODE_CLASS_LUT >> (2 * y_mode)) & 3;
+        const bool skip = mclass != 0 && mclass != 3 && (flags & VP8B200_MBF_SKIP);
+        return s_par[((flags & 3) << 4) | (ref << 2) | mclass] | (skip ? 0x80000000u : 0u);
+    };
+    auto load_rec = [&](int col) -> unsigned { return col < g.mb_cols ? mbrec[col * 4] : 0u; };
+    unsigned par_lane = par_of(load_rec(lane));             /* macroblocks 0..31 */
+    unsigned rec_next = load_rec(32 + lane), par_next = 0;  /* macroblocks 32..63 */
+
+    /* Pixel rows are prefetched LF_PF macroblocks ahead with cp.async into a per-lane
+     * shared-memory ring (lane-private slots: no barrier, only cp.async.wait_group): under
+     * load the L2 / DRAM latency of a row is several iterations long, and a register
+     * prefetch is consumed (moved) one iteration after it was issued. */
+    const unsigned pf_base = (unsigned)__cvta_generic_to_shared(s_pf_w) + lane * 16;
+    auto prefetch = [&](int col) {
+        if (lane_on && col < g.mb_cols) {
+            const unsigned dst = pf_base + (col & (LF_PF - 1)) * 512;
+            if (luma) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rowp + col * 16) : "memory");
+            else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(rowp + col * 8) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto fetch = [&](int col, unsigned (&d)[4]) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(s_pf_w + (col & (LF_PF - 1)) * 512 + lane * 16);
+        d[0] = v.x; d[1] = v.y; d[2] = luma ? v.z : 0u; d[3] = luma ? v.w : 0u;
+    };
+    unsigned cur[4], nxt[4], prev[3] = {0, 0, 0}, halo = 0;
+#pragma unroll
+    for (int i = 0; i < LF_PF; i++) prefetch(i);
+#if LF_START_SLEEP
+    /* a row far down the frame waits a long time for its first message: sleep through the
+     * part of that wait that is certain instead of polling L2 */
+    if (top && !recv_smem) {
+        for (unsigned left = (unsigned)(mb_row / LF_ROWS_PER_CTA) * LF_START_SLEEP; left; ) {
+            const unsigned t = min(left, 500000u);
+            __nanosleep(t);
+            left -= t;
+        }
+    }
+#endif
+    asm volatile("cp.async.wait_group %0;" ::"n"(LF_PF - 1) : "memory");
+    fetch(0, cur);
+
+    /* rows of the macroblock LEFT of x = colp, final once the left edge at colp is filtered */
+    auto store_prev = [&](uint8_t *colp) {
+        if (owns_store) {
+            if (luma) *reinterpret_cast<uint4 *>(colp - 16) = make_uint4(prev[0], prev[1], prev[2], halo);
+            else *reinterpret_cast<uint2 *>(colp - 8) = make_uint2(prev[0], halo);
+        }
+    };
+    TR_DECL;
+    /* message for MB `col` of this row: words of rows keep.. after the next MB's left edge */
+    auto send = [&](int col) {
+        unsigned m[4];
+        if (luma) { m[0] = prev[0]; m[1] = prev[1]; m[2] = prev[2]; m[3] = halo; }
+        else { m[0] = prev[0]; m[1] = halo; m[2] = 0; m[3] = 0; }
+        if (send_smem) {
+            TR(1);
+            while ((int)(col - s_rcvd[warp]) >= LF_RING) { }             /* ring full: wait for the consumer */
+            TR(0);
+            if (sender) {
+                uint8_t *slot = s_ring[warp][col & (LF_RING - 1)] + ss_off;
+                if (luma) *reinterpret_cast<uint4 *>(slot) = make_uint4(m[0], m[1], m[2], m[3]);
+                else *reinterpret_cast<uint2 *>(slot) = make_uint2(m[0], m[1]);
+            }
+            bar_arrive(1 + warp * LF_RING + (col & (LF_RING - 1)));
+        } else if (sender) {
+            g_send(gmsg_out + (size_t)col * 256, m, tag, luma);
+        }
+    };
+
+    for (int c = 0; c < g.mb_cols; c++) {
+        TR(5);
+        if ((c & 31) == 16) par_next = par_of(rec_next);
+        if ((c & 31) == 0 && c) { par_lane = par_next; rec_next = load_rec(c + 32 + lane); }
+        const unsigned par = __shfl_sync(0xffffffffu, par_lane, c & 31);
+        const bool skip_lf = (par >> 31) != 0;
+        const bool level = (par & 255) != 0;               /* ilim >= 1 whenever the level is not 0 */
+        LfParams P;
+        P.ilim = par & 255; P.blim = (par >> 8) & 255; P.mblim = (par >> 16) & 255; P.thr = (par >> 24) & 3;
+        /* the next macroblock's rows have landed (LF_PF - 2 younger groups may be in flight);
+         * its slot is then free for the macroblock LF_PF ahead */
+        asm volatile("cp.async.wait_group %0;" ::"n"(LF_PF - 2) : "memory");
+        fetch(c + 1, nxt);
+        prefetch(c + LF_PF);
+        uint8_t *colp = rowp + c * mbw;                     /* my row at this MB's x = 0 */
+
+        /* ---- vertical edges, lane = pixel row ---- */
+        int x[8];
+        unpack(cur[0], x[0], x[1], x[2], x[3]);
+        if (c > 0) {
+            if (lane_on && level) {
+                int h0, h1, h2, h3;
+                unpack(halo, h0, h1, h2, h3);
+                edge8<true, SIMPLE>(h0, h1, h2, h3, x[0], x[1], x[2], x[3], P);
+                halo = pack(h0, h1, h2, h3);
+            }
+#if LF_EARLY
+            /* the previous MB of this row is now final: store it (one 16- / 8-byte store per
+             * pixel row) and hand its last rows down */
+            store_prev(colp);
+            if (!last_row) send(c - 1);
+#endif
+        }
+        if (lane_on && level) {
+            if (!skip_lf) {
+                /* all lanes run the luma sequence; a chroma lane's third and fourth word are
+                 * zeros and its second word is taken before the edge at x = 8 touches it */
+                int y[8];
+                unpack(cur[1], x[4], x[5], x[6], x[7]);
+                edge8<false, SIMPLE>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7], P);
+                const unsigned c1 = pack(x[4], x[5], x[6], x[7]);
+                if (LF_NODIV || luma) {
+                    unpack(cur[2], y[0], y[1], y[2], y[3]);
+                    edge8<false, SIMPLE>(x[4], x[5], x[6], x[7], y[0], y[1], y[2], y[3], P);
+                    unpack(cur[3], y[4], y[5], y[6], y[7]);
+                    edge8<false, SIMPLE>(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7], P);
+                    cur[1] = luma ? pack(x[4], x[5], x[6], x[7]) : c1;
+                    cur[2] = pack(y[0], y[1], y[2], y[3]);
+                    cur[3] = pack(y[4], y[5], y[6], y[7]);
+                } else {
+                    cur[1] = c1;
+                }
+            }
+            cur[0] = pack(x[0], x[1], x[2], x[3]);
+        }
+#if !LF_EARLY
+        if (c > 0) {
+            store_prev(colp);
+            if (!last_row) send(c - 1);
+        }
+#endif
+        /* ---- the 4 rows above arrive as a message from the row above ---- */
+        TR(1);
+        if (top) {
+            if (recv_smem) {
+                bar_wait(1 + (warp - 1) * LF_RING + (c & (LF_RING - 1)));
+                TR(2);
+                if (receiver) {
+                    const uint8_t *slot = s_ring[warp - 1][c & (LF_RING - 1)] + sr_off;
+                    if (luma) *reinterpret_cast<uint4 *>(tile + pi * 16) = *reinterpret_cast<const uint4 *>(slot);
+                    else *reinterpret_cast<uint2 *>(tile + pi * 8) = *reinterpret_cast<const uint2 *>(slot);
+                }
+                __syncwarp();
+                if (lane == 0) s_rcvd[warp - 1] = (unsigned)c + 1;
+            } else if (receiver) {
+                unsigned m[4];
+                g_recv(gmsg_in + (size_t)c * 256, m, tag, luma);
+                TR(3);
+                if (luma) *reinterpret_cast<uint4 *>(tile + pi * 16) = make_uint4(m[0], m[1], m[2], m[3]);
+                else *reinterpret_cast<uint2 *>(tile + pi * 8) = make_uint2(m[0], m[1]);
+            }
+        }
+        TR(4);
+        if (level) {
+            /* rows the horizontal edges touch: all of them, or only rows 0..3 for the top edge
+             * of a macroblock without inner edges (nothing at all if that has no top either) */
+            const int nrows = skip_lf ? 4 : mbw;            /* MB rows entering the tile */
+            if (lane_on && (!skip_lf || top) && pi < nrows) {
+                if (luma) *reinterpret_cast<uint4 *>(tile + (pi + 4) * 16) = make_uint4(cur[0], cur[1], cur[2], cur[3]);
+                else *reinterpret_cast<uint2 *>(tile + (pi + 4) * 8) = make_uint2(cur[0], cur[1]);
+            }
+            __syncwarp();
+            /* ---- horizontal edges, lane = pixel column ---- */
+            if (lane_on && (!skip_lf || top)) {
+                int v[8];
+                if (top) {
+#pragma unroll
+                    for (int r = 0; r < 8; r++) v[r] = tile[r * mbw + pi];
+                    edge8<true, SIMPLE>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], P);
+#pragma unroll
+                    for (int r = 1; r < 4; r++) tile[r * mbw + pi] = (uint8_t)v[r];
+                    if (skip_lf) {
+#pragma unroll
+                        for (int r = 4; r < 7; r++) tile[r * mbw + pi] = (uint8_t)v[r];
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 4; r < 8; r++) v[r] = tile[r * mbw + pi];
+                }
+                if (!skip_lf) {
+                    /* tile rows 8..11 are the last real rows of a chroma MB: a chroma lane keeps
+                     * them as they are after the first inner edge and plays the two luma-only
+                     * edges on its scratch rows */
+                    int w[8], u[4], wb[4];
+#pragma unroll
+                    for (int r = 0; r < 4; r++) w[r] = tile[(r + 8) * mbw + pi];
+#pragma unroll
+                    for (int r = 4; r < 8; r++) w[r] = tile_hi[(r + 8) * mbw + pi];
+#pragma unroll
+                    for (int r = 0; r < 4; r++) u[r] = tile_hi[(r + 16) * mbw + pi];
+                    edge8<false, SIMPLE>(v[4], v[5], v[6], v[7], w[0], w[1], w[2], w[3], P);
+#pragma unroll
+                    for (int r = 4; r < 8; r++) tile[r * mbw + pi] = (uint8_t)v[r];
+#pragma unroll
+                    for (int r = 0; r < 4; r++) wb[r] = w[r];
+                    if (LF_NODIV || luma) {
+                        edge8<false, SIMPLE>(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], P);
+#pragma unroll
+                        for (int r = 0; r < 4; r++) tile[(r + 8) * mbw + pi] = (uint8_t)(luma ? w[r] : wb[r]);
+                        edge8<false, SIMPLE>(w[4], w[5], w[6], w[7], u[0], u[1], u[2], u[3], P);
+#pragma unroll
+                        for (int r = 4; r < 8; r++) tile_hi[(r + 8) * mbw + pi] = (uint8_t)w[r];
+#pragma unroll
+                        for (int r = 0; r < 4; r++) tile_hi[(r + 16) * mbw + pi] = (uint8_t)u[r];
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 4; r++) tile[(r + 8) * mbw + pi] = (uint8_t)wb[r];
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane_on && (!skip_lf || top) && pi < nrows) {
+                if (luma) { uint4 v = *reinterpret_cast<const uint4 *>(tile + (pi + 4) * 16); cur[0] = v.x; cur[1] = v.y; cur[2] = v.z; cur[3] = v.w; }
+                else { uint2 v = *reinterpret_cast<const uint2 *>(tile + (pi + 4) * 8); cur[0] = v.x; cur[1] = v.y; }
+            }
+        } else {
+            __syncwarp();                                   /* message rows visible in the tile */
+        }
+        /* (this MB's own rows go out one iteration later, after the next MB's left edge) */
+        if (receiver && pi >= 1) {                          /* rows -3..-1: this row finishes them */
+            uint8_t *ap = plane + (size_t)(mb_row * mbw - 4 + pi) * stride + c * mbw;
+            if (luma) *reinterpret_cast<uint4 *>(ap) = *reinterpret_cast<const uint4 *>(tile + pi * 16);
+            else *reinterpret_cast<uint2 *>(ap) = *reinterpret_cast<const uint2 *>(tile + pi * 8);
+        }
+        if (luma) { prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2]; halo = cur[3]; }
+        else { prev[0] = cur[0]; halo = cur[1]; }
+        __syncwarp();                                       /* tile is reused by the next MB */
+#pragma unroll
+        for (int i = 0; i < 4; i++) cur[i] = nxt[i];
+    }
+#ifdef LF_TRACE
+    if (lane == 0 && job.epoch_lf % 8 == 5 && (mb_row % 4 == 0 || mb_row % 4 == 3 || mb_row % 4 == 1) && (size_t)job.dst % 7 == 0)
+        printf("LFT row %d ringfull %lld V+send %lld barwait %lld grecv %lld misc %lld H+store %lld total %lld\n", mb_row,
+               tr_[0], tr_[1], tr_[2], tr_[3], tr_[4], tr_[5], clock64() - tr_start);
+#endif
+    /* the last macroblock of the row */
+    store_prev(rowp + g.mb_cols * mbw);
+    if (!last_row) send(g.mb_cols - 1);
+}
+
+__global__ void __launch_bounds__(LF_ROWS_PER_CTA * 32, LF_MIN_CTAS)
 k_loopfilter(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g,
              unsigned *ticket, const unsigned ticket_base)
 {
     __shared__ FrameJob job;
     __shared__ unsigned s_ticket;
-    __shared__ uint8_t s_lvl[64];                          /* [seg][ref][mode class] */
+    /* [seg][ref][mode class] -> ilim | blim << 8 | mblim << 16 | hev threshold << 24; 0: level 0 */
+    __shared__ unsigned s_par[64];
     __shared__ __align__(16) uint8_t s_tile[LF_ROWS_PER_CTA][512];
+    __shared__ __align__(16) uint8_t s_scratch[LF_ROWS_PER_CTA][384];
+    __shared__ __align__(16) uint8_t s_pf[LF_ROWS_PER_CTA][LF_PF][512];   /* cp.async ring: [slot][lane][16 B] */
     /* message ring of row w -> row w+1: 128 B = luma rows 12..15 (4x16), U 4..7 (4x8), V 4..7 */
     __shared__ __align__(16) uint8_t s_ring[LF_ROWS_PER_CTA][LF_RING][128];
-    __shared__ volatile unsigned s_sent[LF_ROWS_PER_CTA], s_rcvd[LF_ROWS_PER_CTA];
+    __shared__ volatile unsigned s_rcvd[LF_ROWS_PER_CTA];
     if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u) - ticket_base;
-    if (threadIdx.x < LF_ROWS_PER_CTA) { s_sent[threadIdx.x] = 0; s_rcvd[threadIdx.x] = 0; }
+    if (threadIdx.x < LF_ROWS_PER_CTA) s_rcvd[threadIdx.x] = 0;
     __syncthreads();
     const unsigned t = s_ticket;
     const int ji = t % n_jobs, group = t / n_jobs;
@@ -200,252 +526,24 @@ k_loopfilter(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g,
             else lvl += h.mode_lf_deltas[mode];
             lvl = min(max(lvl, 0), 63);
         }
-        s_lvl[threadIdx.x] = (uint8_t)lvl;
+        /* limits of that level: loopfilter.c:66-96 and :28-50 */
+        const int sharp = h.sharpness_level;
+        const bool key = h.frame_type == 0;
+        int il = lvl >> (sharp > 0);
+        il >>= (sharp > 4);
+        if (sharp > 0) il = min(il, 9 - sharp);
+        il = max(il, 1);
+        const int thr = key ? (lvl >= 40 ? 2 : (lvl >= 15 ? 1 : 0))
+                            : (lvl >= 40 ? 3 : (lvl >= 20 ? 2 : (lvl >= 15 ? 1 : 0)));
+        s_par[threadIdx.x] = lvl ? (unsigned)il | (unsigned)(2 * lvl + il) << 8 | (unsigned)(2 * (lvl + 2) + il) << 16 | (unsigned)thr << 24 : 0u;
     }
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mb_row = group * LF_ROWS_PER_CTA + warp;
     if (mb_row >= g.mb_rows) return;
-    const unsigned tag = job.epoch_lf;                     /* marks this frame's global messages */
-    const bool simple = h.filter_type != 0;
-    const bool key = h.frame_type == 0;
-    const int sharp = h.sharpness_level;
-
-    /* lane geometry */
-    const bool luma = lane < 16;
-    const int pi = luma ? lane : (lane & 7);               /* row (V phase) / column (H phase) */
-    const int stride = luma ? g.y_stride : g.uv_stride;
-    const int mbw = luma ? 16 : 8;                         /* MB width = height in this plane */
-    uint8_t *plane = job.dst + (luma ? g.y_off : (lane < 24 ? g.u_off : g.v_off));
-    uint8_t *rowp = plane + (size_t)(mb_row * mbw + pi) * stride;      /* my pixel row, x = 0 */
-    const bool lane_on = luma || !simple;                  /* simple filter: luma only */
-    uint8_t *tile = s_tile[warp] + (luma ? 0 : (lane < 24 ? 320 : 416));
-    const bool top = mb_row > 0;
-    const bool last_row = mb_row == g.mb_rows - 1;
-    /* rows >= keep of every MB (not in the last MB row) are finished and stored by the row
-     * below; this row hands rows keep.. down as a message instead */
-    const int keep = luma ? 12 : 4;
-    const bool owns_store = lane_on && (last_row || pi <= keep);
-    const bool sender = lane_on && !last_row && pi >= keep;
-    const bool receiver = lane_on && top && pi < 4;
-    const bool send_smem = warp < LF_ROWS_PER_CTA - 1;     /* consumer row lives in this CTA */
-    const bool recv_smem = warp > 0;
-    /* global slot offsets */
-    const int gs_off = luma ? (pi - 12) * 32 : (lane < 24 ? 128 : 192) + (pi - 4) * 16;
-    const int gr_off = luma ? pi * 32 : (lane < 24 ? 128 : 192) + pi * 16;
-    uint8_t *gmsg_out = job.lf_msg + (size_t)mb_row * g.mb_cols * 256 + gs_off;
-    const uint8_t *gmsg_in = job.lf_msg + (size_t)(mb_row - 1) * g.mb_cols * 256 + gr_off;
-    /* shared ring offsets */
-    const int ss_off = luma ? (pi - 12) * 16 : (lane < 24 ? 64 : 96) + (pi - 4) * 8;
-    const int sr_off = luma ? pi * 16 : (lane < 24 ? 64 : 96) + pi * 8;
-
-    const unsigned *mbrec = reinterpret_cast<const unsigned *>(job.mb + (size_t)mb_row * g.mb_cols);
-    /* pixel rows are prefetched LF_PF macroblocks ahead: under load the DRAM/L2 latency of a
-     * row is several iterations long */
-    unsigned cur[4] = {0, 0, 0, 0}, pf[LF_PF][4], prev[3] = {0, 0, 0}, halo = 0;
-    auto load_row = [&](int col, unsigned (&d)[4]) {
-        if (lane_on && col < g.mb_cols) {
-            if (luma) { uint4 v = *reinterpret_cast<const uint4 *>(rowp + col * 16); d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
-            else { uint2 v = *reinterpret_cast<const uint2 *>(rowp + col * 8); d[0] = v.x; d[1] = v.y; }
-        }
-    };
-#pragma unroll
-    for (int i = 0; i < LF_PF; i++) { pf[i][0] = pf[i][1] = pf[i][2] = pf[i][3] = 0; }
-    load_row(0, cur);
-#pragma unroll
-    for (int i = 0; i < LF_PF - 1; i++) load_row(i + 1, pf[i]);
-    unsigned rec = mbrec[0], rec_n = 0;
-
-    /* message for MB `col` of this row: words of rows keep.. after the next MB's left edge */
-    auto send = [&](int col) {
-        unsigned m[4];
-        if (luma) { m[0] = prev[0]; m[1] = prev[1]; m[2] = prev[2]; m[3] = halo; }
-        else { m[0] = prev[0]; m[1] = halo; m[2] = 0; m[3] = 0; }
-        if (send_smem) {
-            while ((int)(col - s_rcvd[warp]) >= LF_RING) { }             /* ring full: wait for the consumer */
-            if (sender) {
-                uint8_t *slot = s_ring[warp][col & (LF_RING - 1)] + ss_off;
-                if (luma) *reinterpret_cast<uint4 *>(slot) = make_uint4(m[0], m[1], m[2], m[3]);
-                else *reinterpret_cast<uint2 *>(slot) = make_uint2(m[0], m[1]);
-            }
-#if LF_BAR
-            bar_arrive(1 + warp * LF_RING + (col & (LF_RING - 1)));
-#else
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0) s_sent[warp] = (unsigned)col + 1;
-#endif
-        } else if (sender) {
-            g_send(gmsg_out + (size_t)col * 256, m, tag, luma);
-        }
-    };
-
-    for (int c = 0; c < g.mb_cols; c++) {
-        /* prefetch: the record of the next macroblock, the rows of the one LF_PF ahead */
-        if (c + 1 < g.mb_cols) rec_n = mbrec[(c + 1) * 4];
-        load_row(c + LF_PF, pf[LF_PF - 1]);
-        /* per-MB decisions, loopfilter.c:245-253 */
-        const int y_mode = rec & 255, ref = (rec >> 16) & 255, flags = rec >> 24;
-        const bool skip_lf = y_mode != VP8B200_B_PRED && y_mode != VP8B200_SPLITMV && (flags & VP8B200_MBF_SKIP);
-        /* mode_lf_lut, loopfilter.c:52-63: DC,V,H,TM,ZEROMV -> 1 ; B_PRED -> 0 ; NEAREST,NEAR,NEW -> 2 ; SPLIT -> 3 */
-        const int mclass = y_mode == VP8B200_B_PRED ? 0 : y_mode == VP8B200_SPLITMV ? 3
-                         : (y_mode <= VP8B200_TM_PRED || y_mode == VP8B200_ZEROMV) ? 1 : 2;
-        const int level = s_lvl[((flags & 3) << 4) | (ref << 2) | mclass];
-        uint8_t *colp = rowp + c * mbw;                     /* my row at this MB's x = 0 */
-        LfParams P;
-        {   /* loopfilter.c:66-96 and :28-50 */
-            int il = level >> (sharp > 0);
-            il >>= (sharp > 4);
-            if (sharp > 0) il = min(il, 9 - sharp);
-            il = max(il, 1);
-            P.ilim = il; P.blim = 2 * level + il; P.mblim = 2 * (level + 2) + il;
-            P.thr = key ? (level >= 40 ? 2 : (level >= 15 ? 1 : 0))
-                        : (level >= 40 ? 3 : (level >= 20 ? 2 : (level >= 15 ? 1 : 0)));
-        }
-        /* ---- vertical edges, lane = pixel row, pixels unpacked once ---- */
-        if (lane_on && level) {
-            int x[8];
-            if (c > 0) {
-                int h0, h1, h2, h3;
-                unpack(halo, h0, h1, h2, h3);
-                unpack(cur[0], x[0], x[1], x[2], x[3]);
-                edge8<true>(h0, h1, h2, h3, x[0], x[1], x[2], x[3], simple, P);
-                halo = pack(h0, h1, h2, h3);
-                if (skip_lf) cur[0] = pack(x[0], x[1], x[2], x[3]);
-            } else if (!skip_lf) {
-                unpack(cur[0], x[0], x[1], x[2], x[3]);
-            }
-            if (!skip_lf) {
-                unpack(cur[1], x[4], x[5], x[6], x[7]);
-                edge8<false>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7], simple, P);
-                cur[0] = pack(x[0], x[1], x[2], x[3]);
-                if (luma) {
-                    int y[8];
-                    unpack(cur[2], y[0], y[1], y[2], y[3]);
-                    edge8<false>(x[4], x[5], x[6], x[7], y[0], y[1], y[2], y[3], simple, P);
-                    cur[1] = pack(x[4], x[5], x[6], x[7]);
-                    unpack(cur[3], y[4], y[5], y[6], y[7]);
-                    edge8<false>(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7], simple, P);
-                    cur[2] = pack(y[0], y[1], y[2], y[3]);
-                    cur[3] = pack(y[4], y[5], y[6], y[7]);
-                } else {
-                    cur[1] = pack(x[4], x[5], x[6], x[7]);
-                }
-            }
-        }
-        /* the previous MB of this row is now final: store / hand down its last 4 columns */
-        if (c > 0) {
-            if (owns_store) *reinterpret_cast<unsigned *>(colp - 4) = halo;
-            if (!last_row) send(c - 1);
-        }
-        /* ---- the 4 rows above arrive as a message from the row above ---- */
-        if (top) {
-            if (recv_smem) {
-#if LF_BAR
-                bar_wait(1 + (warp - 1) * LF_RING + (c & (LF_RING - 1)));
-#else
-                for (int tries = 0; s_sent[warp - 1] <= (unsigned)c; tries++) if (tries > 24) __nanosleep(64);   /* spin briefly, then back off */
-                __threadfence_block();
-#endif
-                if (receiver) {
-                    const uint8_t *slot = s_ring[warp - 1][c & (LF_RING - 1)] + sr_off;
-                    if (luma) *reinterpret_cast<uint4 *>(tile + pi * 16) = *reinterpret_cast<const uint4 *>(slot);
-                    else *reinterpret_cast<uint2 *>(tile + pi * 8) = *reinterpret_cast<const uint2 *>(slot);
-                }
-                __syncwarp();
-                if (lane == 0) s_rcvd[warp - 1] = (unsigned)c + 1;
-            } else if (receiver) {
-                unsigned m[4];
-                g_recv(gmsg_in + (size_t)c * 256, m, tag, luma);
-                if (luma) *reinterpret_cast<uint4 *>(tile + pi * 16) = make_uint4(m[0], m[1], m[2], m[3]);
-                else *reinterpret_cast<uint2 *>(tile + pi * 8) = make_uint2(m[0], m[1]);
-            }
-        }
-        if (level) {
-            /* rows the horizontal edges touch: all of them, or only rows 0..3 for the top edge
-             * of a macroblock without inner edges (nothing at all if that has no top either) */
-            const int nrows = skip_lf ? 4 : mbw;            /* MB rows entering the tile */
-            if (lane_on && (!skip_lf || top) && pi < nrows) {
-                if (luma) *reinterpret_cast<uint4 *>(tile + (pi + 4) * 16) = make_uint4(cur[0], cur[1], cur[2], cur[3]);
-                else *reinterpret_cast<uint2 *>(tile + (pi + 4) * 8) = make_uint2(cur[0], cur[1]);
-            }
-            __syncwarp();
-            /* ---- horizontal edges, lane = pixel column ---- */
-            if (lane_on && (!skip_lf || top)) {
-                int v[8];
-                if (top) {
-#pragma unroll
-                    for (int r = 0; r < 8; r++) v[r] = tile[r * mbw + pi];
-                    edge8<true>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], simple, P);
-#pragma unroll
-                    for (int r = 1; r < 4; r++) tile[r * mbw + pi] = (uint8_t)v[r];
-                    if (skip_lf) {
-#pragma unroll
-                        for (int r = 4; r < 7; r++) tile[r * mbw + pi] = (uint8_t)v[r];
-                    }
-                } else {
-#pragma unroll
-                    for (int r = 4; r < 8; r++) v[r] = tile[r * mbw + pi];
-                }
-                if (!skip_lf) {
-                    int w[8];
-#pragma unroll
-                    for (int r = 0; r < 4; r++) w[r] = tile[(r + 8) * mbw + pi];
-                    edge8<false>(v[4], v[5], v[6], v[7], w[0], w[1], w[2], w[3], simple, P);
-#pragma unroll
-                    for (int r = 4; r < 8; r++) tile[r * mbw + pi] = (uint8_t)v[r];
-                    if (luma) {
-#pragma unroll
-                        for (int r = 4; r < 8; r++) w[r] = tile[(r + 8) * mbw + pi];
-                        edge8<false>(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], simple, P);
-#pragma unroll
-                        for (int r = 0; r < 4; r++) tile[(r + 8) * mbw + pi] = (uint8_t)w[r];
-#pragma unroll
-                        for (int r = 0; r < 4; r++) v[r] = tile[(r + 16) * mbw + pi];
-                        edge8<false>(w[4], w[5], w[6], w[7], v[0], v[1], v[2], v[3], simple, P);
-#pragma unroll
-                        for (int r = 4; r < 8; r++) tile[(r + 8) * mbw + pi] = (uint8_t)w[r];
-#pragma unroll
-                        for (int r = 0; r < 4; r++) tile[(r + 16) * mbw + pi] = (uint8_t)v[r];
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < 4; r++) tile[(r + 8) * mbw + pi] = (uint8_t)w[r];
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane_on && (!skip_lf || top) && pi < nrows) {
-                if (luma) { uint4 v = *reinterpret_cast<const uint4 *>(tile + (pi + 4) * 16); cur[0] = v.x; cur[1] = v.y; cur[2] = v.z; cur[3] = v.w; }
-                else { uint2 v = *reinterpret_cast<const uint2 *>(tile + (pi + 4) * 8); cur[0] = v.x; cur[1] = v.y; }
-            }
-        } else {
-            __syncwarp();                                   /* message rows visible in the tile */
-        }
-        /* ---- rows out; the last word waits for the next MB's left edge ---- */
-        if (owns_store) {
-            *reinterpret_cast<unsigned *>(colp) = cur[0];
-            if (luma) { *reinterpret_cast<unsigned *>(colp + 4) = cur[1]; *reinterpret_cast<unsigned *>(colp + 8) = cur[2]; }
-        }
-        if (receiver && pi >= 1) {                          /* rows -3..-1: this row finishes them */
-            uint8_t *ap = plane + (size_t)(mb_row * mbw - 4 + pi) * stride + c * mbw;
-            if (luma) *reinterpret_cast<uint4 *>(ap) = *reinterpret_cast<const uint4 *>(tile + pi * 16);
-            else *reinterpret_cast<uint2 *>(ap) = *reinterpret_cast<const uint2 *>(tile + pi * 8);
-        }
-        if (luma) { prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2]; halo = cur[3]; }
-        else { prev[0] = cur[0]; halo = cur[1]; }
-        __syncwarp();                                       /* tile is reused by the next MB */
-        rec = rec_n;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            cur[i] = pf[0][i];
-#pragma unroll
-            for (int k = 0; k + 1 < LF_PF; k++) pf[k][i] = pf[k + 1][i];
-        }
-    }
-    /* last 4 columns of the row */
-    if (owns_store) *reinterpret_cast<unsigned *>(rowp + g.mb_cols * mbw - 4) = halo;
-    if (!last_row) send(g.mb_cols - 1);
+    if (h.filter_type != 0) lf_row<true>(job, g, mb_row, warp, lane, s_par, s_tile[warp], s_scratch[warp], &s_pf[warp][0][0], s_ring, s_rcvd);
+    else lf_row<false>(job, g, mb_row, warp, lane, s_par, s_tile[warp], s_scratch[warp], &s_pf[warp][0][0], s_ring, s_rcvd);
 }
 
 void vp8b200_launch_loopfilter(cudaStream_t s, const FrameJob *jobs, int n_jobs, const Geo &g,

@@ -4,11 +4,11 @@
 set -e
 name=$1; shift
 cd "$(dirname "$0")/../libvpx.opencl_b200"
-out=_obj/var_$name; mkdir -p $out
+out=_obj/var_$name; rm -rf $out; mkdir -p $out
 NV="/usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -I../include -Icsrc --cudart static"
 for f in runtime kernels_recon kernels_intra kernels_lf kernels_border; do
   $NV "$@" -c csrc/$f.cu -o $out/$f.o &
 done
-wait
+wait; for f in runtime kernels_recon kernels_intra kernels_lf kernels_border; do test -f $out/$f.o || { echo "compile failed: $f"; exit 1; }; done
 $NV -shared -o ../gpurun_variants_$name.so $out/*.o
 echo built gpurun_variants_$name.so
