@@ -148,6 +148,9 @@ __device__ __forceinline__ void edge8(int &p3, int &p2, int &p1, int &p0, int &q
 #ifndef LF_START_SLEEP
 #define LF_START_SLEEP 0          /* ns per row group slept before the first poll (at most half the real lag) */
 #endif
+#ifndef LF_GPF
+#define LF_GPF 0                  /* 1: read the next macroblock's global message one iteration ahead */
+#endif
 #ifndef LF_NODIV
 #define LF_NODIV 1                /* chroma lanes run the luma-only edges on scratch data instead of diverging */
 #endif
@@ -170,22 +173,33 @@ __device__ __forceinline__ void g_send(uint8_t *slot, const unsigned (&m)[4], un
     if (luma) { st_msg2(slot, m[0], m[1], tag); st_msg2(slot + 16, m[2], m[3], tag); }
     else st_msg2(slot, m[0], m[1], tag);
 }
-__device__ __forceinline__ void g_recv(const uint8_t *slot, unsigned (&m)[4], unsigned tag, bool luma)
+/* w holds an earlier read of the slot (the loop prefetches the next macroblock's message while
+ * it works on the current one, so a row that runs a little behind the row above never waits
+ * for L2 here); re-read until every word carries this frame's tag */
+__device__ __forceinline__ void g_load(const uint8_t *slot, unsigned long long (&w)[4], bool luma)
 {
-    unsigned long long a, b, c = 0, d = 0;
+    ld_msg2(slot, w[0], w[1]);
+    if (luma) ld_msg2(slot + 16, w[2], w[3]);
+}
+__device__ __forceinline__ void g_recv(const uint8_t *slot, unsigned long long (&w)[4], unsigned (&m)[4], unsigned tag, bool luma)
+{
     int tries = 0;
     for (;;) {
-        ld_msg2(slot, a, b);
-        if (luma) ld_msg2(slot + 16, c, d);
-        bool ok = (unsigned)(a >> 32) == tag && (unsigned)(b >> 32) == tag;
-        if (luma) ok = ok && (unsigned)(c >> 32) == tag && (unsigned)(d >> 32) == tag;
+        bool ok = (unsigned)(w[0] >> 32) == tag && (unsigned)(w[1] >> 32) == tag;
+        if (luma) ok = ok && (unsigned)(w[2] >> 32) == tag && (unsigned)(w[3] >> 32) == tag;
         if (ok) break;
         if (++tries > 8) __nanosleep(LF_POLL_SLEEP);
+        g_load(slot, w, luma);
     }
-    m[0] = (unsigned)a; m[1] = (unsigned)b; m[2] = (unsigned)c; m[3] = (unsigned)d;
+    m[0] = (unsigned)w[0]; m[1] = (unsigned)w[1]; m[2] = (unsigned)w[2]; m[3] = (unsigned)w[3];
 }
 
-#ifdef LF_TRACE
+#if defined(LF_TRACE) && LF_TRACE == 2
+#include <cstdio>
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TR_DECL unsigned long long g0_ = gtime(), g1_ = 0, g2_ = 0, g3_ = 0
+#define TR(i)
+#elif defined(LF_TRACE)
 #include <cstdio>
 #define TR_DECL long long tr_[6] = {0, 0, 0, 0, 0, 0}, tr_t = clock64(), tr_start = tr_t
 #define TR(i) do { long long n_ = clock64(); tr_[i] += n_ - tr_t; tr_t = n_; } while (0)
@@ -271,6 +285,8 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
         d[0] = v.x; d[1] = v.y; d[2] = luma ? v.z : 0u; d[3] = luma ? v.w : 0u;
     };
     unsigned cur[4], nxt[4], prev[3] = {0, 0, 0}, halo = 0;
+    const unsigned long long no_msg = (unsigned long long)~tag << 32;     /* a word that is not this frame's */
+    unsigned long long gw[4] = {no_msg, no_msg, no_msg, no_msg};          /* last read of the next global message */
 #pragma unroll
     for (int i = 0; i < LF_PF; i++) prefetch(i);
 #if LF_START_SLEEP
@@ -391,12 +407,21 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
                 if (lane == 0) s_rcvd[warp - 1] = (unsigned)c + 1;
             } else if (receiver) {
                 unsigned m[4];
-                g_recv(gmsg_in + (size_t)c * 256, m, tag, luma);
+                g_recv(gmsg_in + (size_t)c * 256, gw, m, tag, luma);
+#if LF_GPF
+                if (c + 1 < g.mb_cols) g_load(gmsg_in + (size_t)(c + 1) * 256, gw, luma);
+#else
+                gw[0] = gw[1] = gw[2] = gw[3] = no_msg;
+#endif
                 TR(3);
                 if (luma) *reinterpret_cast<uint4 *>(tile + pi * 16) = make_uint4(m[0], m[1], m[2], m[3]);
                 else *reinterpret_cast<uint2 *>(tile + pi * 8) = make_uint2(m[0], m[1]);
             }
         }
+#if defined(LF_TRACE) && LF_TRACE == 2
+        if (c == 0) g1_ = gtime();
+        if (c == 60) g2_ = gtime();
+#endif
         TR(4);
         if (level) {
             /* rows the horizontal edges touch: all of them, or only rows 0..3 for the top edge
@@ -475,7 +500,7 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
 #pragma unroll
         for (int i = 0; i < 4; i++) cur[i] = nxt[i];
     }
-#ifdef LF_TRACE
+#if defined(LF_TRACE) && LF_TRACE != 2
     if (lane == 0 && job.epoch_lf % 8 == 5 && (mb_row % 4 == 0 || mb_row % 4 == 3 || mb_row % 4 == 1) && (size_t)job.dst % 7 == 0)
         printf("LFT row %d ringfull %lld V+send %lld barwait %lld grecv %lld misc %lld H+store %lld total %lld\n", mb_row,
                tr_[0], tr_[1], tr_[2], tr_[3], tr_[4], tr_[5], clock64() - tr_start);
@@ -483,6 +508,11 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
     /* the last macroblock of the row */
     store_prev(rowp + g.mb_cols * mbw);
     if (!last_row) send(g.mb_cols - 1);
+#if defined(LF_TRACE) && LF_TRACE == 2
+    g3_ = gtime();
+    if (lane == 0 && job.epoch_lf % 8 == 5 && (size_t)job.dst % 7 == 0)
+        printf("LFT %d %llu %llu %llu %llu\n", mb_row, g0_, g1_, g2_, g3_);
+#endif
 }
 
 __global__ void __launch_bounds__(LF_ROWS_PER_CTA * 32, LF_MIN_CTAS)

@@ -1,4 +1,4 @@
-for v in pf8 pf16 pf8ss pf8ps pf8e pf8c6; do
+for v in gpf r8 base; do
   echo "== $v"
   VP8B200_LIB=$PWD/gpurun_variants_$v.so timeout 120 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -1
   VP8B200_LIB=$PWD/gpurun_variants_$v.so timeout 60 python tools/kernel_times.py --streams 1 --frames 4 2>&1 | tail -2
