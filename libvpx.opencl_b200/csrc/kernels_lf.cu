@@ -149,7 +149,7 @@ __device__ __forceinline__ void edge8(int &p3, int &p2, int &p1, int &p0, int &q
 #define LF_START_SLEEP 0          /* ns per row group slept before the first poll (at most half the real lag) */
 #endif
 #ifndef LF_GPF
-#define LF_GPF 0                  /* 1: read the next macroblock's global message one iteration ahead */
+#define LF_GPF 1                  /* read the next macroblock's global message one iteration ahead (single stream 0.25 -> 0.22 ms) */
 #endif
 #ifndef LF_NODIV
 #define LF_NODIV 1                /* chroma lanes run the luma-only edges on scratch data instead of diverging */
