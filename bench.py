@@ -379,7 +379,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=30)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=64, help="independent streams per GPU")
-    ap.add_argument("--groups", type=int, default=4, help="stream groups batched on separate CUDA streams")
+    ap.add_argument("--groups", type=int, default=2, help="stream groups batched on separate CUDA streams")
     ap.add_argument("--stagger", type=int, default=1,
                     help="1: stream group g plays g*F/G frames ahead (streams out of phase); 0: all streams on the same frame")
     ap.add_argument("--e2e-threads", type=int, default=0)

@@ -67,6 +67,8 @@ RANDOM_CASES = [
     (40, 3, dict(sharpness=7)),
     (33, 2, dict(key=True, coef_density=1.0, big_coefs=True)),
     (80, 45, dict()),                                        # 720p
+    (65, 5, dict(filter_type=1)),                            # record batches of 32 + 32 + 1, simple filter
+    (32, 6, dict(sharpness=3)), (9, 70, dict()),             # exactly one batch; more rows than a CTA wave is deep
 ]
 
 
