@@ -54,6 +54,23 @@ def p_decodframe(l):
     # S3: per-MB record replaces prediction + residual
     i = find_one(l, "/* do prediction */")
     l.insert(i, "    vp8b200_seam_record_mb(pbi, xd, mb_idx);\n    return;\n")
+    # partition-parallel token parse: rows may run on several threads, so the
+    # row function clears the left context it was given, waits for the row above before a
+    # macroblock and publishes the macroblock afterwards; the row loop asks the seam first
+    i = find_one(l, "vpx_memset(&pc->left_context, 0, sizeof(pc->left_context));")
+    l[i] = "    vpx_memset(xd->left_context, 0, sizeof(*xd->left_context));\n"
+    i = find_one(l, "decode_macroblock(pbi, xd, mb_row * pc->mb_cols  + mb_col);")
+    l.insert(i + 1, "        vp8b200_seam_mb_done(mb_row, mb_col);\n")
+    l.insert(i, "        vp8b200_seam_mb_wait(mb_row, mb_col);\n")
+    i = find_one(l, "static unsigned int read_partition_size(const unsigned char *cx_size)")
+    l.insert(i, "static void decode_mb_row_b200(void *pbi, int mb_row, void *xd)\n{\n"
+                "    decode_mb_row((VP8D_COMP *)pbi, &((VP8D_COMP *)pbi)->common, mb_row, (MACROBLOCKD *)xd);\n}\n\n")
+    i = find_one(l, "decode_mb_row(pbi, pc, mb_row, xd);")
+    j = i
+    while "for (mb_row = 0; mb_row < pc->mb_rows; mb_row++)" not in l[j]:
+        j -= 1
+    assert i - j < 16
+    l[j] = l[j].replace("mb_row = 0;", "mb_row = vp8b200_seam_decode_rows(pbi, xd, decode_mb_row_b200) ? pc->mb_rows : 0;")
     # per-row 4-pixel extension: device rule, drop the host call (spans several lines)
     i = find_one(l, "vp8_extend_mb_row(")
     j = i

@@ -11,6 +11,9 @@ void  vp8b200_seam_destroy(struct VP8D_COMP *pbi);
 void  vp8b200_seam_frame_begin(struct VP8D_COMP *pbi);
 int   vp8b200_seam_decode_tokens(struct VP8D_COMP *pbi, struct macroblockd *xd);
 void  vp8b200_seam_record_mb(struct VP8D_COMP *pbi, struct macroblockd *xd, unsigned int mb_idx);
+int   vp8b200_seam_decode_rows(struct VP8D_COMP *pbi, struct macroblockd *xd, void (*row_fn)(void *, int, void *));
+void  vp8b200_seam_mb_wait(int mb_row, int mb_col);
+void  vp8b200_seam_mb_done(int mb_row, int mb_col);
 void  vp8b200_seam_frame_submit(struct VP8D_COMP *pbi);
 void  vp8b200_seam_fetch(struct VP8D_COMP *pbi);
 void  vp8b200_seam_copy_fb(struct VP8D_COMP *pbi, int dst_idx, int src_idx);

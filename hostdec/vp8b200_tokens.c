@@ -145,17 +145,24 @@ static inline int block_tokens(vp8b200_booldec *bd, const uint8_t *type_probs, i
     return c;
 }
 
-int vp8b200_decode_mb_tokens(vp8b200_booldec *bd_io, const uint8_t *probs, signed char *above,
+int vp8b200_decode_mb_tokens(vp8b200_booldec *bd_io, const uint8_t *probs, signed char *above_,
                              signed char *left, int has_y2, int16_t *coef, uint32_t *mask_out)
 {
     enum { TYPE = 8 * 3 * 11 };                   /* bytes per block type */
     /* work on a private copy: stores through the context pointers (char) could alias the
      * caller's struct and would force a reload of the state after every block */
     vp8b200_booldec state = *bd_io, *const bd = &state;
+    /* ... and of the column's context entry (9 bytes, ENTROPY_CONTEXT_PLANES): in the
+     * partition-parallel parser neighbouring columns of the shared array belong to other
+     * threads, and touching it once per macroblock instead of twice per block keeps the
+     * cache line from bouncing */
+    signed char above[9], *const above_io = above_;
     int16_t y2[16];
     uint32_t mask = 0;
     int eobtotal = 0, i, eob, first = 0, have_y2 = 0;
     const uint8_t *tp = probs + 3 * TYPE;         /* type 3: Y with DC */
+
+    memcpy(above, above_io, 9);
 
     if (has_y2) {                                 /* type 1: Y2, decoded first, stored last */
         eob = block_tokens(bd, probs + 1 * TYPE, above[8] + left[8], 0, y2);
@@ -182,6 +189,7 @@ int vp8b200_decode_mb_tokens(vp8b200_booldec *bd_io, const uint8_t *probs, signe
     }
     if (have_y2) { memcpy(coef, y2, 32); mask |= 1u << 24; }
     if (bd->count < 0) refill(bd);                /* detokenize.c:377 */
+    memcpy(above_io, above, 9);
     *bd_io = state;
     *mask_out = mask;
     return eobtotal;

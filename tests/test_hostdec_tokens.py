@@ -215,11 +215,14 @@ def test_token_reader_round_trip(tokens_lib, seed, density, pad):
     assert bd.buf <= base + len(data)
 
 
-def _dump(ivf, path, ref_tokens):
+def _dump(ivf, path, ref_tokens, threads=None):
     env = dict(os.environ, VP8B200_NO_DEVICE="1", VP8B200_DUMP=path)
     env.pop("VP8B200_TOKENS", None)
+    env.pop("VP8B200_PARSE_THREADS", None)
     if ref_tokens:
         env["VP8B200_TOKENS"] = "ref"
+    if threads:
+        env["VP8B200_PARSE_THREADS"] = str(threads)
     subprocess.run([VPXDEC_B200, "--noblit", ivf], env=env, check=True, stdout=subprocess.DEVNULL,
                    stderr=subprocess.DEVNULL, timeout=300)
     return open(path, "rb").read()
@@ -234,3 +237,17 @@ def test_fused_reader_gives_the_reference_records(name):
         new = _dump(ivf, os.path.join(tmp, "new.rec"), False)
     assert new == ref
     assert new == lzma.decompress(open(os.path.join(GOLD, name + ".rec.xz"), "rb").read())
+
+
+@pytest.mark.skipif(not os.path.exists(VPXDEC_B200), reason="hostdec/_build is not built (needs the reference sources)")
+@pytest.mark.parametrize("threads", [2, 3, 8])
+def test_partition_parallel_parse_gives_the_serial_records(threads):
+    """rows of different token partitions parsed on different threads (per-row
+    arena regions, packed afterwards) must give byte-identical records to the serial parser -
+    8 partitions with segmentation (w320_er8); 3 threads = uneven partition-to-thread map."""
+    ivf = os.path.join(GOLD, "w320_er8.ivf")
+    with tempfile.TemporaryDirectory() as tmp:
+        serial = _dump(ivf, os.path.join(tmp, "t1.rec"), False, threads=1)
+        par = _dump(ivf, os.path.join(tmp, "tn.rec"), False, threads=threads)
+    assert par == serial
+    assert par == lzma.decompress(open(os.path.join(GOLD, "w320_er8.rec.xz"), "rb").read())
