@@ -296,6 +296,9 @@ int vp8b200_seam_decode_rows(VP8D_COMP *pbi, MACROBLOCKD *xd, void (*row_fn)(voi
     uint32_t co = 0, ao = 0;
 
     if (!s || !s->open || s->ref_tokens || num_part < 2 || s->parse_threads == 1) return 0;
+    /* per-row regions need the dense worst case per row */
+    if (s->bufs.aux_capacity < (uint32_t)(pc->mb_rows * pc->mb_cols) ||
+        s->bufs.coef_capacity < (uint32_t)(pc->mb_rows * pc->mb_cols) * 25u) return 0;
     n_threads = s->parse_threads > 0 ? s->parse_threads : (int)sysconf(_SC_NPROCESSORS_ONLN);
     if (n_threads > num_part) n_threads = num_part;
     if (n_threads > 8) n_threads = 8;
