@@ -17,3 +17,4 @@ B="python bench.py --steps 4 --warmup 2 --skip-e2e --skip-verify --no-cpu-baseli
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/v8/r01_launches_v8.csv $B > gpurun_out/v8/ncu1.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_loopfilter -s 3 -c 1 -f -o gpurun_out/v8/r01_lf_v8 $B > gpurun_out/v8/ncu2.log 2>&1
 for f in gpurun_out/v8/*.json; do echo "== $f"; cat $f; echo; done
+python tools/config_table.py --out gpurun_out/v8/r01_configs.json > gpurun_out/v8/cfg.log 2>&1; tail -6 gpurun_out/v8/cfg.log | cut -c1-400
