@@ -216,7 +216,7 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 template <bool SIMPLE>
 __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const int mb_row, const int warp, const int lane,
                                        const unsigned *s_par, uint8_t *s_tile_w, uint8_t *s_scratch_w, uint8_t *s_pf_w,
-                                       uint8_t (*s_ring)[LF_RING][128], volatile unsigned *s_rcvd)
+                                       uint8_t (*s_ring)[LF_RING][192], volatile unsigned *s_rcvd)
 {
     const unsigned tag = job.epoch_lf;                     /* marks this frame's global messages */
 
@@ -228,10 +228,12 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
     uint8_t *plane = job.dst + (luma ? g.y_off : (lane < 24 ? g.u_off : g.v_off));
     uint8_t *rowp = plane + (size_t)(mb_row * mbw + pi) * stride;      /* my pixel row, x = 0 */
     const bool lane_on = luma || !SIMPLE;                  /* simple filter: luma only */
-    uint8_t *tile = s_tile_w + (luma ? 0 : (lane < 24 ? 320 : 416));
-    /* tile rows 12.. exist for luma only; chroma lanes run the same (branch-free) code on a
-     * scratch area instead of diverging */
-    uint8_t *tile_hi = luma ? tile : s_scratch_w + (lane < 24 ? 0 : 192);
+    /* tile: 16 bytes per pixel row for every plane (a chroma row uses the first 8), so that
+     * all lanes move rows with the same 16-byte operations: luma rows -4..15 at 0, U rows
+     * -4..7 at 320, V at 512.  Tile rows 12.. exist for luma only; chroma lanes run the same
+     * (branch-free) code on a scratch area instead of diverging */
+    uint8_t *tile = s_tile_w + (luma ? 0 : (lane < 24 ? 320 : 512));
+    uint8_t *tile_hi = luma ? tile : s_scratch_w + (lane < 24 ? 0 : 320);
     const bool top = mb_row > 0;
     const bool last_row = mb_row == g.mb_rows - 1;
     /* rows >= keep of every MB (not in the last MB row) are finished and stored by the row
@@ -248,8 +250,9 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
     uint8_t *gmsg_out = job.lf_msg + (size_t)mb_row * g.mb_cols * 256 + gs_off;
     const uint8_t *gmsg_in = job.lf_msg + (size_t)(mb_row - 1) * g.mb_cols * 256 + gr_off;
     /* shared ring offsets */
-    const int ss_off = luma ? (pi - 12) * 16 : (lane < 24 ? 64 : 96) + (pi - 4) * 8;
-    const int sr_off = luma ? pi * 16 : (lane < 24 ? 64 : 96) + pi * 8;
+    const int ss_off = luma ? (pi - 12) * 16 : (lane < 24 ? 64 : 128) + (pi - 4) * 16;
+    const int sr_off = luma ? pi * 16 : (lane < 24 ? 64 : 128) + pi * 16;
+    const bool own16 = owns_store && luma, own8 = owns_store && !luma;
 
     const unsigned *mbrec = reinterpret_cast<const unsigned *>(job.mb + (size_t)mb_row * g.mb_cols);
     /* Per-MB decisions (loopfilter.c:245-253), 32 macroblocks at a time: lane l loads the first
@@ -273,12 +276,15 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
      * prefetch is consumed (moved) one iteration after it was issued. */
     const unsigned pf_base = (unsigned)__cvta_generic_to_shared(s_pf_w) + lane * 16;
     auto prefetch = [&](int col) {
-        if (lane_on && col < g.mb_cols) {
-            const unsigned dst = pf_base + (col & (LF_PF - 1)) * 512;
-            if (luma) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rowp + col * 16) : "memory");
-            else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(rowp + col * 8) : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        const unsigned dst = pf_base + (col & (LF_PF - 1)) * 512;
+        const int in = col < g.mb_cols;
+        asm volatile("{ .reg .pred p, q;\n\t"
+                     "setp.ne.b32 p, %2, 0;\n\t"
+                     "setp.ne.b32 q, %3, 0;\n\t"
+                     "@p cp.async.ca.shared.global [%0], [%1], 16;\n\t"
+                     "@q cp.async.ca.shared.global [%0], [%1], 8;\n\t"
+                     "cp.async.commit_group; }"
+                     ::"r"(dst), "l"(rowp + col * mbw), "r"((int)(luma && in)), "r"((int)(lane_on && !luma && in)) : "memory");
     };
     auto fetch = [&](int col, unsigned (&d)[4]) {
         const uint4 v = *reinterpret_cast<const uint4 *>(s_pf_w + (col & (LF_PF - 1)) * 512 + lane * 16);
@@ -305,10 +311,8 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
 
     /* rows of the macroblock LEFT of x = colp, final once the left edge at colp is filtered */
     auto store_prev = [&](uint8_t *colp) {
-        if (owns_store) {
-            if (luma) *reinterpret_cast<uint4 *>(colp - 16) = make_uint4(prev[0], prev[1], prev[2], halo);
-            else *reinterpret_cast<uint2 *>(colp - 8) = make_uint2(prev[0], halo);
-        }
+        if (own16) *reinterpret_cast<uint4 *>(colp - 16) = make_uint4(prev[0], prev[1], prev[2], halo);
+        if (own8) *reinterpret_cast<uint2 *>(colp - 8) = make_uint2(prev[0], halo);
     };
     TR_DECL;
     /* message for MB `col` of this row: words of rows keep.. after the next MB's left edge */
@@ -322,8 +326,7 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
             TR(0);
             if (sender) {
                 uint8_t *slot = s_ring[warp][col & (LF_RING - 1)] + ss_off;
-                if (luma) *reinterpret_cast<uint4 *>(slot) = make_uint4(m[0], m[1], m[2], m[3]);
-                else *reinterpret_cast<uint2 *>(slot) = make_uint2(m[0], m[1]);
+                *reinterpret_cast<uint4 *>(slot) = make_uint4(m[0], m[1], m[2], m[3]);
             }
             bar_arrive(1 + warp * LF_RING + (col & (LF_RING - 1)));
         } else if (sender) {
@@ -400,8 +403,7 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
                 TR(2);
                 if (receiver) {
                     const uint8_t *slot = s_ring[warp - 1][c & (LF_RING - 1)] + sr_off;
-                    if (luma) *reinterpret_cast<uint4 *>(tile + pi * 16) = *reinterpret_cast<const uint4 *>(slot);
-                    else *reinterpret_cast<uint2 *>(tile + pi * 8) = *reinterpret_cast<const uint2 *>(slot);
+                    *reinterpret_cast<uint4 *>(tile + pi * 16) = *reinterpret_cast<const uint4 *>(slot);
                 }
                 __syncwarp();
                 if (lane == 0) s_rcvd[warp - 1] = (unsigned)c + 1;
@@ -414,8 +416,7 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
                 gw[0] = gw[1] = gw[2] = gw[3] = no_msg;
 #endif
                 TR(3);
-                if (luma) *reinterpret_cast<uint4 *>(tile + pi * 16) = make_uint4(m[0], m[1], m[2], m[3]);
-                else *reinterpret_cast<uint2 *>(tile + pi * 8) = make_uint2(m[0], m[1]);
+                *reinterpret_cast<uint4 *>(tile + pi * 16) = make_uint4(m[0], m[1], m[2], m[3]);
             }
         }
 #if defined(LF_TRACE) && LF_TRACE == 2
@@ -427,27 +428,25 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
             /* rows the horizontal edges touch: all of them, or only rows 0..3 for the top edge
              * of a macroblock without inner edges (nothing at all if that has no top either) */
             const int nrows = skip_lf ? 4 : mbw;            /* MB rows entering the tile */
-            if (lane_on && (!skip_lf || top) && pi < nrows) {
-                if (luma) *reinterpret_cast<uint4 *>(tile + (pi + 4) * 16) = make_uint4(cur[0], cur[1], cur[2], cur[3]);
-                else *reinterpret_cast<uint2 *>(tile + (pi + 4) * 8) = make_uint2(cur[0], cur[1]);
-            }
+            if (lane_on && (!skip_lf || top) && pi < nrows)
+                *reinterpret_cast<uint4 *>(tile + (pi + 4) * 16) = make_uint4(cur[0], cur[1], cur[2], cur[3]);
             __syncwarp();
             /* ---- horizontal edges, lane = pixel column ---- */
             if (lane_on && (!skip_lf || top)) {
                 int v[8];
                 if (top) {
 #pragma unroll
-                    for (int r = 0; r < 8; r++) v[r] = tile[r * mbw + pi];
+                    for (int r = 0; r < 8; r++) v[r] = tile[r * 16 + pi];
                     edge8<true, SIMPLE>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], P);
 #pragma unroll
-                    for (int r = 1; r < 4; r++) tile[r * mbw + pi] = (uint8_t)v[r];
+                    for (int r = 1; r < 4; r++) tile[r * 16 + pi] = (uint8_t)v[r];
                     if (skip_lf) {
 #pragma unroll
-                        for (int r = 4; r < 7; r++) tile[r * mbw + pi] = (uint8_t)v[r];
+                        for (int r = 4; r < 7; r++) tile[r * 16 + pi] = (uint8_t)v[r];
                     }
                 } else {
 #pragma unroll
-                    for (int r = 4; r < 8; r++) v[r] = tile[r * mbw + pi];
+                    for (int r = 4; r < 8; r++) v[r] = tile[r * 16 + pi];
                 }
                 if (!skip_lf) {
                     /* tile rows 8..11 are the last real rows of a chroma MB: a chroma lane keeps
@@ -455,35 +454,35 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
                      * edges on its scratch rows */
                     int w[8], u[4], wb[4];
 #pragma unroll
-                    for (int r = 0; r < 4; r++) w[r] = tile[(r + 8) * mbw + pi];
+                    for (int r = 0; r < 4; r++) w[r] = tile[(r + 8) * 16 + pi];
 #pragma unroll
-                    for (int r = 4; r < 8; r++) w[r] = tile_hi[(r + 8) * mbw + pi];
+                    for (int r = 4; r < 8; r++) w[r] = tile_hi[(r + 8) * 16 + pi];
 #pragma unroll
-                    for (int r = 0; r < 4; r++) u[r] = tile_hi[(r + 16) * mbw + pi];
+                    for (int r = 0; r < 4; r++) u[r] = tile_hi[(r + 16) * 16 + pi];
                     edge8<false, SIMPLE>(v[4], v[5], v[6], v[7], w[0], w[1], w[2], w[3], P);
 #pragma unroll
-                    for (int r = 4; r < 8; r++) tile[r * mbw + pi] = (uint8_t)v[r];
+                    for (int r = 4; r < 8; r++) tile[r * 16 + pi] = (uint8_t)v[r];
 #pragma unroll
                     for (int r = 0; r < 4; r++) wb[r] = w[r];
                     if (LF_NODIV || luma) {
                         edge8<false, SIMPLE>(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], P);
 #pragma unroll
-                        for (int r = 0; r < 4; r++) tile[(r + 8) * mbw + pi] = (uint8_t)(luma ? w[r] : wb[r]);
+                        for (int r = 0; r < 4; r++) tile[(r + 8) * 16 + pi] = (uint8_t)(luma ? w[r] : wb[r]);
                         edge8<false, SIMPLE>(w[4], w[5], w[6], w[7], u[0], u[1], u[2], u[3], P);
 #pragma unroll
-                        for (int r = 4; r < 8; r++) tile_hi[(r + 8) * mbw + pi] = (uint8_t)w[r];
+                        for (int r = 4; r < 8; r++) tile_hi[(r + 8) * 16 + pi] = (uint8_t)w[r];
 #pragma unroll
-                        for (int r = 0; r < 4; r++) tile_hi[(r + 16) * mbw + pi] = (uint8_t)u[r];
+                        for (int r = 0; r < 4; r++) tile_hi[(r + 16) * 16 + pi] = (uint8_t)u[r];
                     } else {
 #pragma unroll
-                        for (int r = 0; r < 4; r++) tile[(r + 8) * mbw + pi] = (uint8_t)wb[r];
+                        for (int r = 0; r < 4; r++) tile[(r + 8) * 16 + pi] = (uint8_t)wb[r];
                     }
                 }
             }
             __syncwarp();
             if (lane_on && (!skip_lf || top) && pi < nrows) {
-                if (luma) { uint4 v = *reinterpret_cast<const uint4 *>(tile + (pi + 4) * 16); cur[0] = v.x; cur[1] = v.y; cur[2] = v.z; cur[3] = v.w; }
-                else { uint2 v = *reinterpret_cast<const uint2 *>(tile + (pi + 4) * 8); cur[0] = v.x; cur[1] = v.y; }
+                const uint4 v = *reinterpret_cast<const uint4 *>(tile + (pi + 4) * 16);
+                cur[0] = v.x; cur[1] = v.y; cur[2] = v.z; cur[3] = v.w;
             }
         } else {
             __syncwarp();                                   /* message rows visible in the tile */
@@ -492,7 +491,7 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
         if (receiver && pi >= 1) {                          /* rows -3..-1: this row finishes them */
             uint8_t *ap = plane + (size_t)(mb_row * mbw - 4 + pi) * stride + c * mbw;
             if (luma) *reinterpret_cast<uint4 *>(ap) = *reinterpret_cast<const uint4 *>(tile + pi * 16);
-            else *reinterpret_cast<uint2 *>(ap) = *reinterpret_cast<const uint2 *>(tile + pi * 8);
+            else *reinterpret_cast<uint2 *>(ap) = *reinterpret_cast<const uint2 *>(tile + pi * 16);
         }
         if (luma) { prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2]; halo = cur[3]; }
         else { prev[0] = cur[0]; halo = cur[1]; }
@@ -523,11 +522,11 @@ k_loopfilter(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g,
     __shared__ unsigned s_ticket;
     /* [seg][ref][mode class] -> ilim | blim << 8 | mblim << 16 | hev threshold << 24; 0: level 0 */
     __shared__ unsigned s_par[64];
-    __shared__ __align__(16) uint8_t s_tile[LF_ROWS_PER_CTA][512];
-    __shared__ __align__(16) uint8_t s_scratch[LF_ROWS_PER_CTA][384];
+    __shared__ __align__(16) uint8_t s_tile[LF_ROWS_PER_CTA][704];
+    __shared__ __align__(16) uint8_t s_scratch[LF_ROWS_PER_CTA][640];
     __shared__ __align__(16) uint8_t s_pf[LF_ROWS_PER_CTA][LF_PF][512];   /* cp.async ring: [slot][lane][16 B] */
-    /* message ring of row w -> row w+1: 128 B = luma rows 12..15 (4x16), U 4..7 (4x8), V 4..7 */
-    __shared__ __align__(16) uint8_t s_ring[LF_ROWS_PER_CTA][LF_RING][128];
+    /* message ring of row w -> row w+1: 192 B = luma rows 12..15, U rows 4..7, V rows 4..7, 16 B each */
+    __shared__ __align__(16) uint8_t s_ring[LF_ROWS_PER_CTA][LF_RING][192];
     __shared__ volatile unsigned s_rcvd[LF_ROWS_PER_CTA];
     if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u) - ticket_base;
     if (threadIdx.x < LF_ROWS_PER_CTA) s_rcvd[threadIdx.x] = 0;

@@ -1,10 +1,4 @@
-mkdir -p gpurun_out/ab13
-B="python bench.py --skip-e2e --skip-verify --no-cpu-baseline --steps 60 --warmup 5"
-for v in cap2 cap3; do
-  VP8B200_LIB=$PWD/gpurun_variants_$v.so timeout 120 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -1
-  for cfg in "2 1" "4 1"; do
-    set -- $cfg
-    VP8B200_LIB=$PWD/gpurun_variants_$v.so $B --groups $1 --stagger $2 > gpurun_out/ab13/${v}_g$1.json 2> gpurun_out/ab13/${v}_g$1.err
-    python -c "import json;d=json.load(open('gpurun_out/ab13/${v}_g$1.json'));print('$v groups $1 stagger $2:',d['value'],d['ms_per_step'],d['roofline']['achieved'])"
-  done
-done
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py -m gpu -x -q 2>&1 | tail -1
+python tools/kernel_times.py --streams 1 --frames 8 2>&1 | tail -4
+python tools/kernel_times.py --streams 64 --frames 8 2>&1 | tail -5
+python bench.py --skip-e2e --skip-verify --no-cpu-baseline --steps 60 --warmup 5 | python -c "import json,sys;d=json.load(sys.stdin);print('bench:',d['value'],d['ms_per_step'],d['roofline']['achieved'],d['roofline']['ms_per_launch'])"
