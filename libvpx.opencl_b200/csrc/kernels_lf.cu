@@ -340,7 +340,9 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
         if ((c & 31) == 0 && c) { par_lane = par_next; rec_next = load_rec(c + 32 + lane); }
         const unsigned par = __shfl_sync(0xffffffffu, par_lane, c & 31);
         const bool skip_lf = (par >> 31) != 0;
-        const bool level = (par & 255) != 0;               /* ilim >= 1 whenever the level is not 0 */
+        /* A macroblock whose filter level is 0 (loopfilter.c:256 skips it) carries all-zero
+         * limits here: the masks then pass only where every difference is zero, where each
+         * filter is the identity - so it takes the ordinary path and costs no branch. */
         LfParams P;
         P.ilim = par & 255; P.blim = (par >> 8) & 255; P.mblim = (par >> 16) & 255; P.thr = (par >> 24) & 3;
         /* the next macroblock's rows have landed (LF_PF - 2 younger groups may be in flight);
@@ -354,7 +356,7 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
         int x[8];
         unpack(cur[0], x[0], x[1], x[2], x[3]);
         if (c > 0) {
-            if (lane_on && level) {
+            if (lane_on) {
                 int h0, h1, h2, h3;
                 unpack(halo, h0, h1, h2, h3);
                 edge8<true, SIMPLE>(h0, h1, h2, h3, x[0], x[1], x[2], x[3], P);
@@ -367,7 +369,7 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
             if (!last_row) send(c - 1);
 #endif
         }
-        if (lane_on && level) {
+        if (lane_on) {
             if (!skip_lf) {
                 /* all lanes run the luma sequence; a chroma lane's third and fourth word are
                  * zeros and its second word is taken before the edge at x = 8 touches it */
@@ -424,7 +426,7 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
         if (c == 60) g2_ = gtime();
 #endif
         TR(4);
-        if (level) {
+        {
             /* rows the horizontal edges touch: all of them, or only rows 0..3 for the top edge
              * of a macroblock without inner edges (nothing at all if that has no top either) */
             const int nrows = skip_lf ? 4 : mbw;            /* MB rows entering the tile */
@@ -484,8 +486,6 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
                 const uint4 v = *reinterpret_cast<const uint4 *>(tile + (pi + 4) * 16);
                 cur[0] = v.x; cur[1] = v.y; cur[2] = v.z; cur[3] = v.w;
             }
-        } else {
-            __syncwarp();                                   /* message rows visible in the tile */
         }
         /* (this MB's own rows go out one iteration later, after the next MB's left edge) */
         if (receiver && pi >= 1) {                          /* rows -3..-1: this row finishes them */
