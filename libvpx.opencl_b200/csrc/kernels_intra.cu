@@ -35,9 +35,6 @@
 #ifndef INTRA_SLEEP
 #define INTRA_SLEEP 32
 #endif
-#ifndef INTRA_BACKOFF
-#define INTRA_BACKOFF 0           /* n > 0: the sleep doubles every 2^n failed polls (up to 32x) */
-#endif
 #define YS 48             /* luma tile pitch: rows -1..15, cols -16..31 ; index (r+1)*48 + 16 + c */
 #define CS 16             /* chroma tile pitch: rows -1..7, cols -4..11 ; index (r+1)*16 + 4 + c  */
 
@@ -267,14 +264,7 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
                     for (int tries = 0;; tries++) {
                         asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
                         if ((unsigned)(v >> 32) == epoch) break;
-#if INTRA_BACKOFF
-                        /* poll hard first (the hand-off is on the chain), then back off: a warp whose
-                         * neighbour is many wavefront levels away should not spend issue slots and L2
-                         * bandwidth on polling */
-                        if (tries > INTRA_SPIN) __nanosleep(min(INTRA_SLEEP << min((tries - INTRA_SPIN) >> INTRA_BACKOFF, 5), 1000));
-#else
                         if (tries > INTRA_SPIN) __nanosleep(INTRA_SLEEP);   /* poll hard first: the hand-off is on the chain */
-#endif
                     }
                     w = (unsigned)v;
                 } else if (grp == 0) {

@@ -133,26 +133,11 @@ __device__ __forceinline__ void edge8(int &p3, int &p2, int &p1, int &p0, int &q
  * half of the kernel's issue slots (profiles/r01_summary_v8.md).  A barrier id is reused
  * every LF_RING columns; the ring-full check keeps the producer from arriving at a barrier
  * whose previous phase the consumer has not left. */
-#ifndef LF_BAR
-#define LF_BAR 1
-#endif
 #ifndef LF_MIN_CTAS
 #define LF_MIN_CTAS 4
 #endif
-#ifndef LF_EARLY
-#define LF_EARLY 0                /* 1: hand the previous MB down right after the left-edge filter (measured slower under load) */
-#endif
 #ifndef LF_POLL_SLEEP
 #define LF_POLL_SLEEP 100         /* ns between polls of a global message after 8 immediate tries */
-#endif
-#ifndef LF_START_SLEEP
-#define LF_START_SLEEP 0          /* ns per row group slept before the first poll (at most half the real lag) */
-#endif
-#ifndef LF_GPF
-#define LF_GPF 1                  /* read the next macroblock's global message one iteration ahead (single stream 0.25 -> 0.22 ms) */
-#endif
-#ifndef LF_NODIV
-#define LF_NODIV 1                /* chroma lanes run the luma-only edges on scratch data instead of diverging */
 #endif
 __device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void bar_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
@@ -194,19 +179,6 @@ __device__ __forceinline__ void g_recv(const uint8_t *slot, unsigned long long (
     m[0] = (unsigned)w[0]; m[1] = (unsigned)w[1]; m[2] = (unsigned)w[2]; m[3] = (unsigned)w[3];
 }
 
-#if defined(LF_TRACE) && LF_TRACE == 2
-#include <cstdio>
-__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-#define TR_DECL unsigned long long g0_ = gtime(), g1_ = 0, g2_ = 0, g3_ = 0
-#define TR(i)
-#elif defined(LF_TRACE)
-#include <cstdio>
-#define TR_DECL long long tr_[6] = {0, 0, 0, 0, 0, 0}, tr_t = clock64(), tr_start = tr_t
-#define TR(i) do { long long n_ = clock64(); tr_[i] += n_ - tr_t; tr_t = n_; } while (0)
-#else
-#define TR_DECL
-#define TR(i)
-#endif
 
 /* mode_lf_lut, loopfilter.c:52-63, two bits per y_mode: DC,V,H,TM,ZEROMV -> 1 ; B_PRED -> 0 ;
  * NEARESTMV,NEARMV,NEWMV -> 2 ; SPLITMV -> 3 */
@@ -295,17 +267,6 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
     unsigned long long gw[4] = {no_msg, no_msg, no_msg, no_msg};          /* last read of the next global message */
 #pragma unroll
     for (int i = 0; i < LF_PF; i++) prefetch(i);
-#if LF_START_SLEEP
-    /* a row far down the frame waits a long time for its first message: sleep through the
-     * part of that wait that is certain instead of polling L2 */
-    if (top && !recv_smem) {
-        for (unsigned left = (unsigned)(mb_row / LF_ROWS_PER_CTA) * LF_START_SLEEP; left; ) {
-            const unsigned t = min(left, 500000u);
-            __nanosleep(t);
-            left -= t;
-        }
-    }
-#endif
     asm volatile("cp.async.wait_group %0;" ::"n"(LF_PF - 1) : "memory");
     fetch(0, cur);
 
@@ -314,16 +275,13 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
         if (own16) *reinterpret_cast<uint4 *>(colp - 16) = make_uint4(prev[0], prev[1], prev[2], halo);
         if (own8) *reinterpret_cast<uint2 *>(colp - 8) = make_uint2(prev[0], halo);
     };
-    TR_DECL;
     /* message for MB `col` of this row: words of rows keep.. after the next MB's left edge */
     auto send = [&](int col) {
         unsigned m[4];
         if (luma) { m[0] = prev[0]; m[1] = prev[1]; m[2] = prev[2]; m[3] = halo; }
         else { m[0] = prev[0]; m[1] = halo; m[2] = 0; m[3] = 0; }
         if (send_smem) {
-            TR(1);
             while ((int)(col - s_rcvd[warp]) >= LF_RING) { }             /* ring full: wait for the consumer */
-            TR(0);
             if (sender) {
                 uint8_t *slot = s_ring[warp][col & (LF_RING - 1)] + ss_off;
                 *reinterpret_cast<uint4 *>(slot) = make_uint4(m[0], m[1], m[2], m[3]);
@@ -335,7 +293,6 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
     };
 
     for (int c = 0; c < g.mb_cols; c++) {
-        TR(5);
         if ((c & 31) == 16) par_next = par_of(rec_next);
         if ((c & 31) == 0 && c) { par_lane = par_next; rec_next = load_rec(c + 32 + lane); }
         const unsigned par = __shfl_sync(0xffffffffu, par_lane, c & 31);
@@ -362,12 +319,6 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
                 edge8<true, SIMPLE>(h0, h1, h2, h3, x[0], x[1], x[2], x[3], P);
                 halo = pack(h0, h1, h2, h3);
             }
-#if LF_EARLY
-            /* the previous MB of this row is now final: store it (one 16- / 8-byte store per
-             * pixel row) and hand its last rows down */
-            store_prev(colp);
-            if (!last_row) send(c - 1);
-#endif
         }
         if (lane_on) {
             if (!skip_lf) {
@@ -377,32 +328,24 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
                 unpack(cur[1], x[4], x[5], x[6], x[7]);
                 edge8<false, SIMPLE>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7], P);
                 const unsigned c1 = pack(x[4], x[5], x[6], x[7]);
-                if (LF_NODIV || luma) {
-                    unpack(cur[2], y[0], y[1], y[2], y[3]);
-                    edge8<false, SIMPLE>(x[4], x[5], x[6], x[7], y[0], y[1], y[2], y[3], P);
-                    unpack(cur[3], y[4], y[5], y[6], y[7]);
-                    edge8<false, SIMPLE>(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7], P);
-                    cur[1] = luma ? pack(x[4], x[5], x[6], x[7]) : c1;
-                    cur[2] = pack(y[0], y[1], y[2], y[3]);
-                    cur[3] = pack(y[4], y[5], y[6], y[7]);
-                } else {
-                    cur[1] = c1;
-                }
+                unpack(cur[2], y[0], y[1], y[2], y[3]);
+                edge8<false, SIMPLE>(x[4], x[5], x[6], x[7], y[0], y[1], y[2], y[3], P);
+                unpack(cur[3], y[4], y[5], y[6], y[7]);
+                edge8<false, SIMPLE>(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7], P);
+                cur[1] = luma ? pack(x[4], x[5], x[6], x[7]) : c1;
+                cur[2] = pack(y[0], y[1], y[2], y[3]);
+                cur[3] = pack(y[4], y[5], y[6], y[7]);
             }
             cur[0] = pack(x[0], x[1], x[2], x[3]);
         }
-#if !LF_EARLY
         if (c > 0) {
             store_prev(colp);
             if (!last_row) send(c - 1);
         }
-#endif
         /* ---- the 4 rows above arrive as a message from the row above ---- */
-        TR(1);
         if (top) {
             if (recv_smem) {
                 bar_wait(1 + (warp - 1) * LF_RING + (c & (LF_RING - 1)));
-                TR(2);
                 if (receiver) {
                     const uint8_t *slot = s_ring[warp - 1][c & (LF_RING - 1)] + sr_off;
                     *reinterpret_cast<uint4 *>(tile + pi * 16) = *reinterpret_cast<const uint4 *>(slot);
@@ -412,20 +355,10 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
             } else if (receiver) {
                 unsigned m[4];
                 g_recv(gmsg_in + (size_t)c * 256, gw, m, tag, luma);
-#if LF_GPF
                 if (c + 1 < g.mb_cols) g_load(gmsg_in + (size_t)(c + 1) * 256, gw, luma);
-#else
-                gw[0] = gw[1] = gw[2] = gw[3] = no_msg;
-#endif
-                TR(3);
                 *reinterpret_cast<uint4 *>(tile + pi * 16) = make_uint4(m[0], m[1], m[2], m[3]);
             }
         }
-#if defined(LF_TRACE) && LF_TRACE == 2
-        if (c == 0) g1_ = gtime();
-        if (c == 60) g2_ = gtime();
-#endif
-        TR(4);
         {
             /* rows the horizontal edges touch: all of them, or only rows 0..3 for the top edge
              * of a macroblock without inner edges (nothing at all if that has no top either) */
@@ -466,19 +399,14 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
                     for (int r = 4; r < 8; r++) tile[r * 16 + pi] = (uint8_t)v[r];
 #pragma unroll
                     for (int r = 0; r < 4; r++) wb[r] = w[r];
-                    if (LF_NODIV || luma) {
-                        edge8<false, SIMPLE>(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], P);
+                    edge8<false, SIMPLE>(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], P);
 #pragma unroll
-                        for (int r = 0; r < 4; r++) tile[(r + 8) * 16 + pi] = (uint8_t)(luma ? w[r] : wb[r]);
-                        edge8<false, SIMPLE>(w[4], w[5], w[6], w[7], u[0], u[1], u[2], u[3], P);
+                    for (int r = 0; r < 4; r++) tile[(r + 8) * 16 + pi] = (uint8_t)(luma ? w[r] : wb[r]);
+                    edge8<false, SIMPLE>(w[4], w[5], w[6], w[7], u[0], u[1], u[2], u[3], P);
 #pragma unroll
-                        for (int r = 4; r < 8; r++) tile_hi[(r + 8) * 16 + pi] = (uint8_t)w[r];
+                    for (int r = 4; r < 8; r++) tile_hi[(r + 8) * 16 + pi] = (uint8_t)w[r];
 #pragma unroll
-                        for (int r = 0; r < 4; r++) tile_hi[(r + 16) * 16 + pi] = (uint8_t)u[r];
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < 4; r++) tile[(r + 8) * 16 + pi] = (uint8_t)wb[r];
-                    }
+                    for (int r = 0; r < 4; r++) tile_hi[(r + 16) * 16 + pi] = (uint8_t)u[r];
                 }
             }
             __syncwarp();
@@ -499,19 +427,9 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
 #pragma unroll
         for (int i = 0; i < 4; i++) cur[i] = nxt[i];
     }
-#if defined(LF_TRACE) && LF_TRACE != 2
-    if (lane == 0 && job.epoch_lf % 8 == 5 && (mb_row % 4 == 0 || mb_row % 4 == 3 || mb_row % 4 == 1) && (size_t)job.dst % 7 == 0)
-        printf("LFT row %d ringfull %lld V+send %lld barwait %lld grecv %lld misc %lld H+store %lld total %lld\n", mb_row,
-               tr_[0], tr_[1], tr_[2], tr_[3], tr_[4], tr_[5], clock64() - tr_start);
-#endif
     /* the last macroblock of the row */
     store_prev(rowp + g.mb_cols * mbw);
     if (!last_row) send(g.mb_cols - 1);
-#if defined(LF_TRACE) && LF_TRACE == 2
-    g3_ = gtime();
-    if (lane == 0 && job.epoch_lf % 8 == 5 && (size_t)job.dst % 7 == 0)
-        printf("LFT %d %llu %llu %llu %llu\n", mb_row, g0_, g1_, g2_, g3_);
-#endif
 }
 
 __global__ void __launch_bounds__(LF_ROWS_PER_CTA * 32, LF_MIN_CTAS)

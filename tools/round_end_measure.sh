@@ -1,4 +1,6 @@
-# round-end measurement set: tests, smoke, e2e CPU split, both bench arms, ncu launch list + LF capture
+# round-end measurement set (run under gpurun): GPU tests, smoke, e2e CPU split, both bench arms,
+# ncu launch list + one full capture of k_loopfilter, per-config table. Outputs: gpurun_out/v8/ ->
+# the ones that are evidence are copied to profiles/ by hand.
 mkdir -p gpurun_out/v8
 python -m pytest tests -m gpu -q > gpurun_out/v8/tests.log 2>&1; echo "tests rc=$? $(tail -1 gpurun_out/v8/tests.log)"
 python __graft_entry__.py smoke > gpurun_out/v8/smoke.log 2>&1; echo "smoke rc=$? $(tail -1 gpurun_out/v8/smoke.log)"
