@@ -184,6 +184,17 @@ int main(int argc, char **argv)
     if (g_threads > g_streams) g_threads = g_streams;
     if (g_threads > 1024) g_threads = 1024;
     g_inst = (inst_t *)calloc((size_t)g_streams, sizeof(inst_t));
+    if (g_threads > 1) {
+        /* the reference initialises its static tables on the first decoded frame behind a plain
+         * flag (vp8dx_initialize, onyxd_if.c:60-70): do that once before the workers start */
+        inst_t prime;
+        vpx_codec_dec_cfg_t cfg = {0};
+        memset(&prime, 0, sizeof prime);
+        prime.clip = &g_clips[0];
+        if (vpx_codec_dec_init(&prime.dec, vpx_codec_vp8_dx(), &cfg, 0)) { fprintf(stderr, "init failed\n"); return 3; }
+        if (prime.clip->nframes) decode_one(&prime, 0, NULL, NULL);
+        vpx_codec_destroy(&prime.dec);
+    }
     pthread_barrier_init(&g_bar, NULL, (unsigned)g_threads);
     for (i = 0; i < g_threads; i++) pthread_create(&th[i], NULL, worker, (void *)(intptr_t)i);
     /* stats snapshot is taken by differencing around the whole run minus warm-up: the
