@@ -251,3 +251,41 @@ def test_partition_parallel_parse_gives_the_serial_records(threads):
         par = _dump(ivf, os.path.join(tmp, "tn.rec"), False, threads=threads)
     assert par == serial
     assert par == lzma.decompress(open(os.path.join(GOLD, "w320_er8.rec.xz"), "rb").read())
+
+
+def _damaged(data, mod):
+    """IVF with per-frame payloads rewritten by mod(index, payload)."""
+    import struct
+    out, pos, i = bytearray(data[:32]), 32, 0
+    while pos + 12 <= len(data):
+        n = struct.unpack("<I", data[pos:pos + 4])[0]
+        hdr, payload = data[pos:pos + 12], data[pos + 12:pos + 12 + n]
+        pos += 12 + n
+        payload = mod(i, payload)
+        out += struct.pack("<I", len(payload)) + hdr[4:] + payload
+        i += 1
+    return bytes(out)
+
+
+@pytest.mark.skipif(not os.path.exists(VPXDEC_B200), reason="hostdec/_build is not built (needs the reference sources)")
+@pytest.mark.parametrize("case", ["truncated_p_frame", "truncated_key_frame", "flipped_bytes"])
+def test_partition_parallel_parse_on_damaged_streams(case):
+    """Truncated partitions and corrupt tokens must end the same way with the serial and the
+    partition-parallel parser: same exit status, same records for the frames that decode."""
+    data = open(os.path.join(GOLD, "w320_er8.ivf"), "rb").read()
+    mod = {"truncated_p_frame": lambda i, f: f[:len(f) * 6 // 10] if i == 3 else f,
+           "truncated_key_frame": lambda i, f: f[:len(f) // 2] if i == 0 else f,
+           "flipped_bytes": lambda i, f: f[:len(f) // 2] + bytes([f[len(f) // 2] ^ 0x55]) + f[len(f) // 2 + 1:]
+           if i in (2, 5) else f}[case]
+    with tempfile.TemporaryDirectory() as tmp:
+        ivf = os.path.join(tmp, "damaged.ivf")
+        open(ivf, "wb").write(_damaged(data, mod))
+        got = {}
+        for threads in (1, 8):
+            dump = os.path.join(tmp, "t%d.rec" % threads)
+            env = dict(os.environ, VP8B200_NO_DEVICE="1", VP8B200_DUMP=dump, VP8B200_PARSE_THREADS=str(threads))
+            env.pop("VP8B200_TOKENS", None)
+            r = subprocess.run([VPXDEC_B200, "--noblit", ivf], env=env, stdout=subprocess.DEVNULL,
+                               stderr=subprocess.DEVNULL, timeout=300)
+            got[threads] = (r.returncode, open(dump, "rb").read() if os.path.exists(dump) else b"")
+    assert got[1] == got[8]
