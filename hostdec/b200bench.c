@@ -10,7 +10,9 @@
  * first creates its decoders and decodes one warm-up pass (device allocations, clocks),
  * then all workers meet at a barrier and decode `repeat` timed passes of their clips.
  *
- * usage: b200bench [--threads T] [--streams S] [--repeat R] [--sum] a.ivf [b.ivf ...]
+ * usage: b200bench [--threads T] [--streams S] [--repeat R] [--sum] [--pipeline] a.ivf [b.ivf ...]
+ *   --pipeline : a worker collects an instance's frame (vpx_codec_get_frame) only after it has
+ *           parsed the next frame of its other instances, so it never waits for the device
  *   --sum : print a byte-sum of every visible frame of instance 0's last pass (cheap check
  *           that pixels really arrive in host memory)
  * prints one JSON line.
@@ -29,7 +31,7 @@
 typedef struct { uint8_t *data; size_t size; int nframes; size_t *off; uint32_t *len; } clip_t;
 typedef struct { vpx_codec_ctx_t dec; const clip_t *clip; int ready; } inst_t;
 
-static int g_threads = 1, g_streams = 1, g_repeat = 1, g_sum = 0, g_nclips = 0;
+static int g_threads = 1, g_streams = 1, g_repeat = 1, g_sum = 0, g_nclips = 0, g_pipeline = 0;
 static clip_t g_clips[1024];
 static inst_t *g_inst;
 static pthread_barrier_t g_bar;
@@ -93,19 +95,26 @@ static void load_clip(clip_t *c, const char *path)
     }
 }
 
-static long decode_one(inst_t *in, int f, uint64_t *sum, double *cpu)
+/* vpx_codec_decode of frame f: parse on the host, records to the device, kernels queued */
+static void submit_one(inst_t *in, int f, double *cpu)
 {
     const clip_t *c = in->clip;
-    vpx_codec_iter_t it = NULL;
-    vpx_image_t *img;
-    long shown = 0;
-    double c0 = cpu ? cpu_s() : 0, c1;
+    double c0 = cpu ? cpu_s() : 0;
     if (vpx_codec_decode(&in->dec, c->data + c->off[f], c->len[f], NULL, 0)) {
         fprintf(stderr, "decode failed: %s (%s)\n", vpx_codec_error(&in->dec),
                 vpx_codec_error_detail(&in->dec) ? vpx_codec_error_detail(&in->dec) : "");
         exit(3);
     }
-    if (cpu) { c1 = cpu_s(); cpu[0] += c1 - c0; c0 = c1; }
+    if (cpu) cpu[0] += cpu_s() - c0;
+}
+
+/* vpx_codec_get_frame until empty: waits for the device, frame arrives in host memory */
+static long drain_one(inst_t *in, uint64_t *sum, double *cpu)
+{
+    vpx_codec_iter_t it = NULL;
+    vpx_image_t *img;
+    long shown = 0;
+    double c0 = cpu ? cpu_s() : 0;
     while ((img = vpx_codec_get_frame(&in->dec, &it))) {
         shown++;
         if (sum) {
@@ -131,6 +140,12 @@ static long decode_one(inst_t *in, int f, uint64_t *sum, double *cpu)
     return shown;
 }
 
+static long decode_one(inst_t *in, int f, uint64_t *sum, double *cpu)
+{
+    submit_one(in, f, cpu);
+    return drain_one(in, sum, cpu);
+}
+
 static void *worker(void *arg)
 {
     int t = (int)(intptr_t)arg, i, f, r, maxf = 0;
@@ -153,9 +168,22 @@ static void *worker(void *arg)
     g_runq[t] = -runq_s();
     for (r = 0; r < g_repeat; r++)
         for (f = 0; f < maxf; f++)
-            for (i = t; i < g_streams; i += g_threads)
-                if (f < g_inst[i].clip->nframes)
-                    n += decode_one(&g_inst[i], f, (g_sum && i == 0 && r == g_repeat - 1) ? &g_checksum : NULL, cpu);
+            for (i = t; i < g_streams; i += g_threads) {
+                inst_t *in = &g_inst[i];
+                uint64_t *sum = (g_sum && i == 0 && r == g_repeat - 1) ? &g_checksum : NULL;
+                if (f >= in->clip->nframes) continue;
+                if (!g_pipeline) { n += decode_one(in, f, sum, cpu); continue; }
+                /* --pipeline: a worker that owns several instances collects an instance's frame
+                 * only when it comes back to that instance, i.e. after it has parsed a frame of
+                 * each of its other instances - by then the device has finished and
+                 * vpx_codec_get_frame does not block.  Per instance the call order is still
+                 * decode, get_frame, decode, ... (the image stays valid until the next decode). */
+                if (in->ready) n += drain_one(in, (g_sum && i == 0 && in->ready == 2) ? &g_checksum : NULL, cpu);
+                submit_one(in, f, cpu);
+                in->ready = r == g_repeat - 1 ? 2 : 1;       /* 2: a frame of the last pass is pending */
+            }
+    for (i = t; i < g_streams; i += g_threads)
+        if (g_inst[i].ready) { n += drain_one(&g_inst[i], (g_sum && i == 0 && g_inst[i].ready == 2) ? &g_checksum : NULL, cpu); g_inst[i].ready = 0; }
     g_t1[t] = now_s();
     g_cpu_dec[t] = cpu[0]; g_cpu_get[t] = cpu[1];
     g_runq[t] += runq_s();
@@ -178,6 +206,7 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[i], "--streams") && i + 1 < argc) g_streams = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--repeat") && i + 1 < argc) g_repeat = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--sum")) g_sum = 1;
+        else if (!strcmp(argv[i], "--pipeline")) g_pipeline = 1;
         else if (g_nclips < 1024) load_clip(&g_clips[g_nclips++], argv[i]);
     }
     if (!g_nclips) { fprintf(stderr, "usage: b200bench [--threads T] [--streams S] [--repeat R] [--sum] a.ivf ...\n"); return 2; }
