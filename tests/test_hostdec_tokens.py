@@ -289,3 +289,27 @@ def test_partition_parallel_parse_on_damaged_streams(case):
                                stderr=subprocess.DEVNULL, timeout=300)
             got[threads] = (r.returncode, open(dump, "rb").read() if os.path.exists(dump) else b"")
     assert got[1] == got[8]
+
+
+VPXENC = os.path.join(ROOT, "oracle", "_ref", "vpxenc")
+
+
+@pytest.mark.skipif(not (os.path.exists(VPXDEC_B200) and os.path.exists(VPXENC)),
+                    reason="hostdec/_build or oracle/_ref is not built (needs the reference sources)")
+@pytest.mark.parametrize("token_parts,threads", [(1, 2), (2, 3), (2, 4), (3, 5)])
+def test_partition_parallel_parse_other_partition_counts(token_parts, threads):
+    """2, 4 and 8 token partitions encoded on the spot by the reference's vpxenc (a frame only 9
+    macroblock rows high, so some threads get one row or none): the partition-parallel parser
+    must reproduce the serial records."""
+    import sys
+    with tempfile.TemporaryDirectory() as tmp:
+        y4m, ivf = os.path.join(tmp, "in.y4m"), os.path.join(tmp, "in.ivf")
+        subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_y4m.py"), "--kind", "motion", "--size",
+                        "208x144", "--frames", "8", "--seed", str(40 + token_parts), "-o", y4m], check=True)
+        subprocess.run([VPXENC, "--ivf", "--rt", "--cpu-used=4", "--token-parts=%d" % token_parts,
+                        "--target-bitrate=400", "-o", ivf, y4m], check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL, timeout=300)
+        serial = _dump(ivf, os.path.join(tmp, "t1.rec"), False, threads=1)
+        par = _dump(ivf, os.path.join(tmp, "tn.rec"), False, threads=threads)
+        ref = _dump(ivf, os.path.join(tmp, "ref.rec"), True)
+    assert len(serial) > 1000 and par == serial == ref
