@@ -88,9 +88,21 @@ def p_onyxd_if(l):
     b = find_one(l, "vp8_yv12_extend_frame_borders_ptr(cm->frame_to_show);")
     assert a < b
     l[a:b + 1] = ["        vp8b200_seam_frame_submit(pbi);\n"]
-    # get_raw_frame: refresh the host mirror of the shown buffer
+    # get_raw_frame: only QUEUE the device->host copy of the shown buffer; the
+    # wait sits in vp8_get_frame.  Frame-delay mode is handled by the seam at the entry.
     i = find_one(l, "*sd = *pbi->common.frame_to_show;")
-    l.insert(i, "        vp8b200_seam_fetch(pbi);\n")
+    l[i] = "        if (vp8b200_seam_show(pbi, sd)) return -1;\n"
+    i = find_one(l, "int ret = -1;")
+    l.insert(i + 1, "    { int r_ = vp8b200_seam_get_raw_frame(pbi, sd, time_stamp, time_end_stamp); if (r_ != 1) return r_; }\n")
+    # decode(NULL, 0) is the flush request in frame-delay mode, not a lost frame
+    i = find_one(l, "if (!pbi->ec_active &&")
+    l.insert(i, "    if (pbi->num_fragments <= 1 && pbi->fragment_sizes[0] == 0 && vp8b200_seam_flush(pbi))\n"
+                "    {\n        pbi->num_fragments = 0;\n        return 0;\n    }\n")
+    # VP8_COPY_REFERENCE / VP8_SET_REFERENCE: the device owns the pixels
+    i = find_one(l, "vp8_yv12_copy_frame_ptr(&cm->yv12_fb[ref_fb_idx], sd);")
+    l[i] = "    {\n        if (vp8b200_seam_sync_fb(pbi, ref_fb_idx)) return pbi->common.error.error_code;\n" + l[i] + "    }\n"
+    i = find_one(l, "vp8_yv12_copy_frame_ptr(sd, &cm->yv12_fb[*ref_fb_ptr]);")
+    l.insert(i + 1, "        if (vp8b200_seam_upload_fb(pbi, *ref_fb_ptr)) return pbi->common.error.error_code;\n")
     i = find_one(l, "vp8_remove_common(&pbi->common);")
     l.insert(i, "    vp8b200_seam_destroy(pbi);\n")
     # missing-frame path: device-side copy next to the host copy
@@ -99,6 +111,19 @@ def p_onyxd_if(l):
     while ");" not in l[j]:
         j += 1
     l.insert(j + 1, "            vp8b200_seam_copy_fb(pbi, cm->lst_fb_idx, prev_idx);\n")
+
+
+def p_dx_iface(l):
+    i = find_one(l, '#include "decoder/onyxd_int.h"')
+    l.insert(i + 1, INC)
+    # vpx_codec_get_frame is where the caller waits for the device
+    i = find_one(l, "img = &ctx->img;")
+    l.insert(i, "            if (vp8b200_seam_wait((struct VP8D_COMP *)ctx->pbi))\n"
+                "            {\n                ctx->img_avail = 0;\n                return NULL;\n            }\n")
+    # a device failure while queueing the copy is a decode error, not "no frame"
+    i = find_one(l, "ctx->img_avail = 1;")
+    assert l[i + 1].strip() == "}"
+    l.insert(i + 2, "        if (!res)\n            res = update_error_state(ctx, &((struct VP8D_COMP *)ctx->pbi)->common.error);\n")
 
 
 def p_yv12config(l):
@@ -130,6 +155,7 @@ def main():
     patch(os.path.join(out, "vp8/decoder/decodframe.c"), p_decodframe)
     patch(os.path.join(out, "vp8/decoder/onyxd_if.c"), p_onyxd_if)
     patch(os.path.join(out, "vpx_scale/generic/yv12config.c"), p_yv12config)
+    patch(os.path.join(out, "vp8/vp8_dx_iface.c"), p_dx_iface)
     print("apply_seams: patched host decoder in", out)
 
 

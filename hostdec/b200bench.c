@@ -10,11 +10,18 @@
  * first creates its decoders and decodes one warm-up pass (device allocations, clocks),
  * then all workers meet at a barrier and decode `repeat` timed passes of their clips.
  *
- * usage: b200bench [--threads T] [--streams S] [--repeat R] [--sum] [--pipeline] a.ivf [b.ivf ...]
+ * usage: b200bench [--threads T] [--streams S] [--repeat R] [--touch] [--sum] [--pipeline] [--delay] a.ivf [b.ivf ...]
+ *   --touch : read every visible pixel of EVERY frame of every instance (a byte sum, printed as
+ *           "checksum") - exactly what oracle/_ref/refbench --touch does on the reference arm,
+ *           so both arms of bench.py consume their frames the same way
  *   --pipeline : a worker collects an instance's frame (vpx_codec_get_frame) only after it has
- *           parsed the next frame of its other instances, so it never waits for the device
- *   --sum : print a byte-sum of every visible frame of instance 0's last pass (cheap check
- *           that pixels really arrive in host memory)
+ *           parsed the next frame of its other instances.  vpx_codec_decode only queues the
+ *           device work (the wait sits in vpx_codec_get_frame), so a worker with several
+ *           instances never waits for the device
+ *   --delay : opt-in frame-delay mode of the decoder (VP8B200_FRAME_DELAY=1): get_frame after
+ *           decode(N) returns frame N-1, decode(NULL, 0) flushes; one instance then overlaps
+ *           its own host parse with its own device reconstruction
+ *   --sum : byte-sum only of instance 0's last pass (cheap check that pixels really arrive)
  * prints one JSON line.
  */
 #define _GNU_SOURCE
@@ -31,7 +38,8 @@
 typedef struct { uint8_t *data; size_t size; int nframes; size_t *off; uint32_t *len; } clip_t;
 typedef struct { vpx_codec_ctx_t dec; const clip_t *clip; int ready; } inst_t;
 
-static int g_threads = 1, g_streams = 1, g_repeat = 1, g_sum = 0, g_nclips = 0, g_pipeline = 0;
+static int g_threads = 1, g_streams = 1, g_repeat = 1, g_sum = 0, g_nclips = 0, g_pipeline = 0, g_touch = 0, g_delay = 0;
+static uint64_t g_tsum[1024];                      /* per-worker --touch sums */
 static clip_t g_clips[1024];
 static inst_t *g_inst;
 static pthread_barrier_t g_bar;
@@ -151,6 +159,7 @@ static void *worker(void *arg)
     int t = (int)(intptr_t)arg, i, f, r, maxf = 0;
     long n = 0;
     double cpu[2] = {0, 0};
+    uint64_t tsum = 0;
     for (i = t; i < g_streams; i += g_threads) {
         vpx_codec_dec_cfg_t cfg = {0};
         inst_t *in = &g_inst[i];
@@ -162,6 +171,11 @@ static void *worker(void *arg)
     for (f = 0; f < maxf; f++)
         for (i = t; i < g_streams; i += g_threads)
             if (f < g_inst[i].clip->nframes) decode_one(&g_inst[i], f, NULL, NULL);
+    if (g_delay)
+        for (i = t; i < g_streams; i += g_threads) {
+            vpx_codec_decode(&g_inst[i].dec, NULL, 0, NULL, 0);
+            drain_one(&g_inst[i], NULL, NULL);
+        }
     pthread_barrier_wait(&g_bar);
     if (t == 0) g_t0 = now_s();
     pthread_barrier_wait(&g_bar);
@@ -170,7 +184,7 @@ static void *worker(void *arg)
         for (f = 0; f < maxf; f++)
             for (i = t; i < g_streams; i += g_threads) {
                 inst_t *in = &g_inst[i];
-                uint64_t *sum = (g_sum && i == 0 && r == g_repeat - 1) ? &g_checksum : NULL;
+                uint64_t *sum = g_touch ? &tsum : (g_sum && i == 0 && r == g_repeat - 1) ? &g_checksum : NULL;
                 if (f >= in->clip->nframes) continue;
                 if (!g_pipeline) { n += decode_one(in, f, sum, cpu); continue; }
                 /* --pipeline: a worker that owns several instances collects an instance's frame
@@ -178,13 +192,19 @@ static void *worker(void *arg)
                  * each of its other instances - by then the device has finished and
                  * vpx_codec_get_frame does not block.  Per instance the call order is still
                  * decode, get_frame, decode, ... (the image stays valid until the next decode). */
-                if (in->ready) n += drain_one(in, (g_sum && i == 0 && in->ready == 2) ? &g_checksum : NULL, cpu);
+                if (in->ready) n += drain_one(in, g_touch ? &tsum : (g_sum && i == 0 && in->ready == 2) ? &g_checksum : NULL, cpu);
                 submit_one(in, f, cpu);
                 in->ready = r == g_repeat - 1 ? 2 : 1;       /* 2: a frame of the last pass is pending */
             }
     for (i = t; i < g_streams; i += g_threads)
-        if (g_inst[i].ready) { n += drain_one(&g_inst[i], (g_sum && i == 0 && g_inst[i].ready == 2) ? &g_checksum : NULL, cpu); g_inst[i].ready = 0; }
+        if (g_inst[i].ready) { n += drain_one(&g_inst[i], g_touch ? &tsum : (g_sum && i == 0 && g_inst[i].ready == 2) ? &g_checksum : NULL, cpu); g_inst[i].ready = 0; }
+    if (g_delay)                                   /* flush the picture every decoder still holds */
+        for (i = t; i < g_streams; i += g_threads) {
+            if (vpx_codec_decode(&g_inst[i].dec, NULL, 0, NULL, 0)) { fprintf(stderr, "flush failed\n"); exit(3); }
+            n += drain_one(&g_inst[i], g_touch ? &tsum : (g_sum && i == 0) ? &g_checksum : NULL, cpu);
+        }
     g_t1[t] = now_s();
+    g_tsum[t] = tsum;
     g_cpu_dec[t] = cpu[0]; g_cpu_get[t] = cpu[1];
     g_runq[t] += runq_s();
     g_frames[t] = n;
@@ -207,6 +227,8 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[i], "--repeat") && i + 1 < argc) g_repeat = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--sum")) g_sum = 1;
         else if (!strcmp(argv[i], "--pipeline")) g_pipeline = 1;
+        else if (!strcmp(argv[i], "--touch")) g_touch = 1;
+        else if (!strcmp(argv[i], "--delay")) { g_delay = 1; setenv("VP8B200_FRAME_DELAY", "1", 1); }
         else if (g_nclips < 1024) load_clip(&g_clips[g_nclips++], argv[i]);
     }
     if (!g_nclips) { fprintf(stderr, "usage: b200bench [--threads T] [--streams S] [--repeat R] [--sum] a.ivf ...\n"); return 2; }
@@ -233,6 +255,7 @@ int main(int argc, char **argv)
     vp8b200_global_stats(st1);
     for (i = 0; i < g_threads; i++) {
         total += g_frames[i]; cpu_dec += g_cpu_dec[i]; cpu_get += g_cpu_get[i];
+        if (g_touch) g_checksum += g_tsum[i];
         runq += g_runq[i]; thread_wall += g_t1[i] - g_t0;
         if (g_t1[i] > tend) tend = g_t1[i];
     }
@@ -242,12 +265,14 @@ int main(int argc, char **argv)
         printf("{\"frames\": %ld, \"wall_s\": %.6f, \"fps\": %.3f, \"threads\": %d, \"streams\": %d, "
                "\"repeat\": %d, \"h2d_bytes\": %.0f, \"d2h_bytes\": %.0f, \"kernel_launches\": %.0f, "
                "\"cpu_ms_per_frame_decode\": %.4f, \"cpu_ms_per_frame_get_frame\": %.4f, "
-               "\"runq_wait_ms_per_frame\": %.4f, \"blocked_ms_per_frame\": %.4f, \"checksum\": %llu}\n",
+               "\"runq_wait_ms_per_frame\": %.4f, \"blocked_ms_per_frame\": %.4f, \"touch\": %d, \"pipeline\": %d, "
+               "\"frame_delay\": %d, \"checksum\": %llu}\n",
                total, tend - g_t0, total / (tend - g_t0), g_threads, g_streams, g_repeat,
                (double)(st1[0] - st0[0]) * share, (double)(st1[1] - st0[1]) * share,
                (double)(st1[2] - st0[2]) * share, 1e3 * cpu_dec / (total ? total : 1),
                1e3 * cpu_get / (total ? total : 1), 1e3 * runq / (total ? total : 1),
-               1e3 * (thread_wall - cpu_dec - cpu_get - runq) / (total ? total : 1), (unsigned long long)g_checksum);
+               1e3 * (thread_wall - cpu_dec - cpu_get - runq) / (total ? total : 1), g_touch, g_pipeline, g_delay,
+               (unsigned long long)g_checksum);
     }
     return 0;
 }

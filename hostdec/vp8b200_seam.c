@@ -14,7 +14,11 @@
  *   vp8/decoder/decodframe.c:191   "do prediction" .. :304    -> vp8b200_seam_record_mb
  *   vp8/decoder/decodframe.c:430   vp8_extend_mb_row          -> (dropped; device rule)
  *   vp8/decoder/onyxd_if.c:576-607 loop filter + extend       -> vp8b200_seam_frame_submit
- *   vp8/decoder/onyxd_if.c:729     *sd = *frame_to_show       -> vp8b200_seam_fetch
+ *   vp8/decoder/onyxd_if.c:729     *sd = *frame_to_show       -> vp8b200_seam_show (queues the D2H, no wait)
+ *   vp8/vp8_dx_iface.c:497         img = &ctx->img            -> vp8b200_seam_wait (vpx_codec_get_frame waits)
+ *   vp8/decoder/onyxd_if.c:709     vp8dx_get_raw_frame entry  -> vp8b200_seam_get_raw_frame (frame-delay mode)
+ *   vp8/decoder/onyxd_if.c:375     missing-frame path         -> vp8b200_seam_flush (decode(NULL,0) = flush)
+ *   vp8/decoder/onyxd_if.c:186,226 VP8_COPY/SET_REFERENCE     -> vp8b200_seam_sync_fb / vp8b200_seam_upload_fb
  *   vp8/decoder/onyxd_if.c:390     vp8_yv12_copy_frame_ptr    -> vp8b200_seam_copy_fb
  *   vp8/decoder/onyxd_if.c:155     vp8_remove_common          -> vp8b200_seam_destroy
  *   vpx_scale/generic/yv12config.c:92,27  vpx_memalign/free   -> vp8b200_seam_alloc/free
@@ -28,6 +32,11 @@
  *   VP8B200_PARSE_THREADS=<n>  threads of the partition-parallel token parser for streams
  *                          with several token partitions (default: one per partition, at
  *                          most 8 and the number of online cores; 1 = serial)
+ *   VP8B200_FRAME_DELAY=1  opt-in one-frame-delay mode: vpx_codec_get_frame after
+ *                          decode(N) returns frame N-1, so the host parses frame N+1 while the
+ *                          device reconstructs frame N; decode(NULL, 0) flushes the last frame
+ *   VP8B200_FETCH=full     copy the whole allocation (borders included) instead of the visible
+ *                          samples only
  *   VP8B200_NO_DEVICE=1    record-capture only: no device is touched and NO pixels are
  *                          produced (frames handed back are undefined).  Exists so that
  *                          golden .rec fixtures can be produced on a machine without a GPU;
@@ -87,6 +96,19 @@ typedef struct seam_state {
     struct seam_mt *mt;           /* partition-parallel parser, created on first use */
     /* host-memory record buffers for VP8B200_NO_DEVICE */
     vp8b200_mb *h_mb; vp8b200_aux *h_aux; int16_t *h_coef;
+    /* lazy fetch: queued in vp8dx_get_raw_frame, waited for in vp8_get_frame */
+    int fetch_full;               /* VP8B200_FETCH=full */
+    int fetch_pending;            /* a fetch_begin nobody has waited for yet */
+    int fetch_fb;                 /* its frame buffer index */
+    int device_failed;            /* sticky: a device call failed, every later frame is an error */
+    /* frame-delay mode: pictures are copied to two private pinned images in turn */
+    int frame_delay;
+    uint8_t *out_buf[2];
+    size_t out_size;
+    int out_cur;
+    int delayed_valid;
+    YV12_BUFFER_CONFIG delayed_sd;
+    int64_t delayed_ts;
 } seam_state;
 
 static void seam_fail(VP8D_COMP *pbi, const char *what, int status)
@@ -103,13 +125,20 @@ static seam_state *seam_get(VP8D_COMP *pbi)
     if (!s) {
         const char *e;
         s = (seam_state *)calloc(1, sizeof *s);
-        if (!s) vpx_internal_error(&pbi->common.error, VPX_CODEC_MEM_ERROR, "vp8b200: seam state");
+        if (!s) {
+            vpx_internal_error(&pbi->common.error, VPX_CODEC_MEM_ERROR, "vp8b200: seam state");
+            return NULL;                         /* only reached when no setjmp is armed */
+        }
         e = getenv("VP8B200_NO_DEVICE");
         s->no_device = e && atoi(e);
         e = getenv("VP8B200_TOKENS");
         s->ref_tokens = e && !strcmp(e, "ref");
         e = getenv("VP8B200_PARSE_THREADS");
         s->parse_threads = e ? atoi(e) : 0;
+        e = getenv("VP8B200_FRAME_DELAY");
+        s->frame_delay = e && atoi(e) && !s->no_device;
+        e = getenv("VP8B200_FETCH");
+        s->fetch_full = e && !strcmp(e, "full");
         e = getenv("VP8B200_DUMP");
         if (e && *e) {
             char path[1024];
@@ -406,20 +435,46 @@ void vp8b200_seam_mb_done(int mb_row, int mb_col)
         __atomic_store_n(&mt->progress[mb_row * MT_PAD], mb_col + 1, __ATOMIC_RELEASE);
 }
 
+/* Frame-buffer memory (yv12config.c:92,27).  Page-locked so that the fetch is a DMA; the kind
+ * of allocation is remembered in a 64-byte header in front of the block, so freeing does not
+ * depend on the environment at that time. */
+#define SEAM_HDR 64
+#define SEAM_PINNED 0x50494e44u   /* "PIND" */
+#define SEAM_MALLOC 0x4d414c43u   /* "MALC" */
+static int seam_device(void)
+{
+    const char *e = getenv("VP8B200_DEVICE");
+    return e ? atoi(e) : 0;
+}
+
 void *vp8b200_seam_alloc(size_t bytes)
 {
     const char *e = getenv("VP8B200_NO_DEVICE");
+    uint8_t *p = NULL;
+    uint32_t kind;
     if (e && atoi(e)) {
-        void *p = NULL;
-        return posix_memalign(&p, 64, bytes) ? NULL : p;
+        void *q = NULL;
+        if (posix_memalign(&q, 64, bytes + SEAM_HDR)) return NULL;
+        p = (uint8_t *)q; kind = SEAM_MALLOC;
+    } else {
+        p = (uint8_t *)vp8b200_host_alloc_on(seam_device(), bytes + SEAM_HDR);
+        if (!p) return NULL;
+        kind = SEAM_PINNED;
     }
-    return vp8b200_host_alloc(bytes);
+    memcpy(p, &kind, sizeof kind);
+    return p + SEAM_HDR;
 }
 
-void vp8b200_seam_free(void *p)
+void vp8b200_seam_free(void *ptr)
 {
-    const char *e = getenv("VP8B200_NO_DEVICE");
-    if (e && atoi(e)) free(p); else vp8b200_host_free(p);
+    uint8_t *p = (uint8_t *)ptr;
+    uint32_t kind;
+    if (!p) return;
+    p -= SEAM_HDR;
+    memcpy(&kind, p, sizeof kind);
+    if (kind == SEAM_PINNED) vp8b200_host_free(p);
+    else if (kind == SEAM_MALLOC) free(p);
+    /* anything else was not allocated here: leave it alone */
 }
 
 void vp8b200_seam_destroy(VP8D_COMP *pbi)
@@ -428,6 +483,7 @@ void vp8b200_seam_destroy(VP8D_COMP *pbi)
     if (!s) return;
     seam_mt_destroy(s);
     if (s->ctx) vp8b200_destroy(s->ctx);
+    vp8b200_host_free(s->out_buf[0]); vp8b200_host_free(s->out_buf[1]);
     if (s->dump) fclose(s->dump);
     free(s->h_mb); free(s->h_aux); free(s->h_coef);
     free(s);
@@ -458,16 +514,21 @@ void vp8b200_seam_frame_begin(VP8D_COMP *pbi)
     uint32_t n_mb = (uint32_t)(pc->mb_rows * pc->mb_cols);
     vp8b200_frame_hdr *hd = &s->hdr;
 
+    if (!s) return;
+    if (s->device_failed)
+        vpx_internal_error(&pc->error, VPX_CODEC_ERROR, "vp8b200: the device failed on an earlier frame");
     if (s->open && s->ctx) vp8b200_frame_abort(s->ctx);   /* frame abandoned by a longjmp */
     s->open = 0;
 
     if (s->width != w || s->height != h) {                /* first frame or size change */
         if (s->ctx) { vp8b200_destroy(s->ctx); s->ctx = NULL; }
+        s->fetch_pending = 0;                             /* destroy waited for the device */
+        vp8b200_host_free(s->out_buf[0]); vp8b200_host_free(s->out_buf[1]);
+        s->out_buf[0] = s->out_buf[1] = NULL;
         free(s->h_mb); free(s->h_aux); free(s->h_coef);
         s->h_mb = NULL; s->h_aux = NULL; s->h_coef = NULL;
         if (!s->no_device) {
-            const char *e = getenv("VP8B200_DEVICE");
-            st = vp8b200_create(&s->ctx, e ? atoi(e) : 0, w, h, NUM_YV12_BUFFERS);
+            st = vp8b200_create(&s->ctx, seam_device(), w, h, NUM_YV12_BUFFERS);
             if (st) seam_fail(pbi, "vp8b200_create", st);
             if ((int)vp8b200_y_stride(s->ctx) != pc->yv12_fb[0].y_stride ||
                 vp8b200_frame_size(s->ctx) != (size_t)pc->yv12_fb[0].frame_size)
@@ -663,16 +724,157 @@ void vp8b200_seam_frame_submit(VP8D_COMP *pbi)
     }
 }
 
-/* vp8dx_get_raw_frame (onyxd_if.c:707-745): make the host mirror of the shown buffer valid */
-void vp8b200_seam_fetch(VP8D_COMP *pbi)
+/* A device call failed outside the decoder's setjmp scope (vp8dx_get_raw_frame / vp8_get_frame
+ * run after vp8dx_receive_compressed_data has returned): record the error where
+ * vp8_decode / the next frame will find it, mark the picture corrupt - never hand out a stale
+ * image as if it were this frame. */
+static int seam_device_error(VP8D_COMP *pbi, seam_state *s, const char *what, int status)
+{
+    VP8_COMMON *cm = &pbi->common;
+    s->device_failed = 1;
+    s->fetch_pending = 0;
+    s->delayed_valid = 0;
+    if (cm->frame_to_show) cm->frame_to_show->corrupted = 1;
+    cm->error.setjmp = 0;
+    seam_fail(pbi, what, status);              /* no longjmp: only records code + detail */
+    return -1;
+}
+
+static int seam_queue_fetch(VP8D_COMP *pbi, seam_state *s, uint8_t *dst)
+{
+    VP8_COMMON *cm = &pbi->common;
+    const int fb = (int)(cm->frame_to_show - cm->yv12_fb);
+    int st = vp8b200_frame_fetch_begin(s->ctx, fb, dst, s->fetch_full ? 0 : cm->Width, s->fetch_full ? 0 : cm->Height);
+    if (st) return seam_device_error(pbi, s, "vp8b200_frame_fetch_begin", st);
+    s->fetch_pending = 1;
+    s->fetch_fb = fb;
+    return 0;
+}
+
+/* vp8dx_get_raw_frame (onyxd_if.c:729), default mode: hand out the shown buffer's host mirror
+ * and only QUEUE its device->host copy; vpx_codec_decode returns while the device is still
+ * reconstructing, vpx_codec_get_frame (vp8b200_seam_wait) is where the caller waits. */
+int vp8b200_seam_show(VP8D_COMP *pbi, YV12_BUFFER_CONFIG *sd)
+{
+    seam_state *s = (seam_state *)pbi->b200_seam;
+    VP8_COMMON *cm = &pbi->common;
+    *sd = *cm->frame_to_show;
+    if (!s || !s->ctx) return 0;               /* record-capture mode: no pixels */
+    if (s->device_failed) return -1;
+    return seam_queue_fetch(pbi, s, cm->frame_to_show->buffer_alloc);
+}
+
+/* vp8_get_frame (vp8_dx_iface.c:485-503): the image is about to be handed to the caller */
+int vp8b200_seam_wait(VP8D_COMP *pbi)
+{
+    seam_state *s = pbi ? (seam_state *)pbi->b200_seam : NULL;
+    int st;
+    if (!s || !s->ctx) return 0;
+    if (s->device_failed) return -1;
+    if (!s->fetch_pending || s->frame_delay) return 0;   /* delay mode waits one call later */
+    s->fetch_pending = 0;
+    st = vp8b200_frame_fetch_wait(s->ctx);
+    if (st) return seam_device_error(pbi, s, "vp8b200_frame_fetch_wait", st);
+    return 0;
+}
+
+/* Entry of vp8dx_get_raw_frame (onyxd_if.c:707).  Returns 1 when the reference's own body
+ * should run (default mode).  In frame-delay mode it does the whole job: the picture decoded
+ * by THIS call is queued for copy into a private pinned image and the picture of the PREVIOUS
+ * call - whose copy has had a whole host parse to finish - is handed out (0), or -1 when there
+ * is none yet.  decode(NULL, 0) (vp8b200_seam_flush) drains the last one. */
+int vp8b200_seam_get_raw_frame(VP8D_COMP *pbi, YV12_BUFFER_CONFIG *sd, int64_t *time_stamp, int64_t *time_end_stamp)
+{
+    seam_state *s = (seam_state *)pbi->b200_seam;
+    VP8_COMMON *cm = &pbi->common;
+    int have_prev, ret = -1;
+    if (!s || !s->frame_delay || !s->ctx) return 1;
+    if (s->device_failed) return -1;
+    have_prev = s->delayed_valid;
+    if (have_prev) {
+        int st = 0;
+        if (s->fetch_pending) { s->fetch_pending = 0; st = vp8b200_frame_fetch_wait(s->ctx); }
+        if (st) return seam_device_error(pbi, s, "vp8b200_frame_fetch_wait", st);
+        *sd = s->delayed_sd;
+        *time_stamp = s->delayed_ts;
+        *time_end_stamp = 0;
+        s->delayed_valid = 0;
+        ret = 0;
+    }
+    if (pbi->ready_for_new_data == 0) {            /* a frame was decoded by this call */
+        pbi->ready_for_new_data = 1;
+        if (cm->show_frame && cm->frame_to_show) {
+            const YV12_BUFFER_CONFIG *f = cm->frame_to_show;
+            uint8_t *out;
+            if (!s->out_buf[0] || s->out_size != (size_t)f->frame_size) {
+                vp8b200_host_free(s->out_buf[0]); vp8b200_host_free(s->out_buf[1]);
+                s->out_buf[0] = (uint8_t *)vp8b200_host_alloc_on(seam_device(), (size_t)f->frame_size);
+                s->out_buf[1] = (uint8_t *)vp8b200_host_alloc_on(seam_device(), (size_t)f->frame_size);
+                s->out_size = (size_t)f->frame_size;
+                if (!s->out_buf[0] || !s->out_buf[1]) return seam_device_error(pbi, s, "pinned output image", VP8B200_ERR_NOMEM);
+            }
+            out = s->out_buf[s->out_cur];
+            s->out_cur ^= 1;
+            if (seam_queue_fetch(pbi, s, out)) return -1;
+            s->delayed_sd = *f;
+            s->delayed_sd.buffer_alloc = out;
+            s->delayed_sd.y_buffer = out + (f->y_buffer - f->buffer_alloc);
+            s->delayed_sd.u_buffer = out + (f->u_buffer - f->buffer_alloc);
+            s->delayed_sd.v_buffer = out + (f->v_buffer - f->buffer_alloc);
+            s->delayed_sd.y_width = cm->Width;
+            s->delayed_sd.y_height = cm->Height;
+            s->delayed_sd.uv_height = cm->Height / 2;
+            s->delayed_sd.clrtype = cm->clr_type;
+            s->delayed_ts = pbi->last_time_stamp;
+            s->delayed_valid = 1;
+        }
+    }
+    return ret;
+}
+
+/* vp8dx_receive_compressed_data with no data (onyxd_if.c:336-373): in frame-delay mode that
+ * is the flush request, not a lost frame */
+int vp8b200_seam_flush(VP8D_COMP *pbi)
+{
+    seam_state *s = (seam_state *)pbi->b200_seam;
+    return s && s->frame_delay && s->delayed_valid;
+}
+
+/* VP8_COPY_REFERENCE (vp8dx_get_reference, onyxd_if.c:161-189): the host mirror of a reference
+ * buffer is not kept current (only visible samples of shown frames are fetched), so bring the
+ * whole buffer over before the reference's host-side copy reads it. */
+int vp8b200_seam_sync_fb(VP8D_COMP *pbi, int idx)
 {
     seam_state *s = (seam_state *)pbi->b200_seam;
     VP8_COMMON *cm = &pbi->common;
     int st;
-    if (!s || !s->ctx || !cm->frame_to_show) return;
-    st = vp8b200_frame_fetch(s->ctx, (int)(cm->frame_to_show - cm->yv12_fb),
-                             cm->frame_to_show->buffer_alloc, (size_t)cm->frame_to_show->frame_size);
-    if (st) seam_fail(pbi, "vp8b200_frame_fetch", st);
+    if (!s || s->no_device) return 0;
+    if (!s->ctx || s->device_failed) {
+        vpx_internal_error(&cm->error, VPX_CODEC_ERROR, "vp8b200: no device frame to copy the reference from");
+        return -1;
+    }
+    if (s->fetch_pending) { s->fetch_pending = 0; vp8b200_frame_fetch_wait(s->ctx); }
+    st = vp8b200_frame_fetch(s->ctx, idx, cm->yv12_fb[idx].buffer_alloc, (size_t)cm->yv12_fb[idx].frame_size);
+    if (st) return seam_device_error(pbi, s, "vp8b200_frame_fetch", st);
+    return 0;
+}
+
+/* VP8_SET_REFERENCE (vp8dx_set_reference, onyxd_if.c:192-230): the reference's host-side copy
+ * (which also extends the borders) has filled the mirror of buffer idx; the device copy is
+ * what later frames predict from. */
+int vp8b200_seam_upload_fb(VP8D_COMP *pbi, int idx)
+{
+    seam_state *s = (seam_state *)pbi->b200_seam;
+    VP8_COMMON *cm = &pbi->common;
+    int st;
+    if (!s || s->no_device) return 0;
+    if (!s->ctx || s->device_failed) {
+        vpx_internal_error(&cm->error, VPX_CODEC_ERROR, "vp8b200: no device context to set the reference in");
+        return -1;
+    }
+    st = vp8b200_frame_upload(s->ctx, idx, cm->yv12_fb[idx].buffer_alloc, (size_t)cm->yv12_fb[idx].frame_size);
+    if (st) return seam_device_error(pbi, s, "vp8b200_frame_upload", st);
+    return 0;
 }
 
 /* onyxd_if.c:390: the missing-frame path moves `last` to its own buffer */

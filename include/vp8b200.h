@@ -157,6 +157,7 @@ int  vp8b200_y_stride(const vp8b200_ctx *ctx);
 
 /* page-locked host memory for the decoder's own YV12 mirrors (so frame_fetch is one DMA) */
 void *vp8b200_host_alloc(size_t bytes);
+void *vp8b200_host_alloc_on(int device, size_t bytes);   /* same, after selecting `device` */
 void  vp8b200_host_free(void *p);
 
 /* ---- per frame ---------------------------------------------------------------------------- */
@@ -169,6 +170,16 @@ int vp8b200_frame_submit(vp8b200_ctx *ctx, uint32_t n_aux, uint32_t n_coef);
 int vp8b200_frame_abort(vp8b200_ctx *ctx);
 /* Wait for frame buffer `fb` and copy the whole allocation (borders included) to `dst`. */
 int vp8b200_frame_fetch(vp8b200_ctx *ctx, int fb, uint8_t *dst, size_t bytes);
+/* Lazy fetch (binds at vp8dx_get_raw_frame, onyxd_if.c:707-745, and
+ * vp8_get_frame, vp8_dx_iface.c:485-503).  fetch_begin queues the device->host copy of frame
+ * buffer `fb` behind the frame's kernels and returns at once; fetch_wait blocks until the
+ * pixels are in host memory.  `dst` is the host image of the WHOLE allocation (the decoder's
+ * YV12 mirror, buffer_alloc): with display_w/h > 0 only the visible samples are copied
+ * (display_w x display_h luma, ((w+1)/2) x ((h+1)/2) chroma - what vpx_codec_get_frame's
+ * caller may read, vpxdec.c:1093-1115), each to the offset it has in the allocation;
+ * display_w == display_h == 0 copies the whole allocation, borders included. */
+int vp8b200_frame_fetch_begin(vp8b200_ctx *ctx, int fb, uint8_t *dst, int display_w, int display_h);
+int vp8b200_frame_fetch_wait(vp8b200_ctx *ctx);
 /* Upload a whole frame buffer (VP8_SET_REFERENCE, onyxd_if.c:161-230). */
 int vp8b200_frame_upload(vp8b200_ctx *ctx, int fb, const uint8_t *src, size_t bytes);
 /* Device-side copy fb_src -> fb_dst (vp8_yv12_copy_frame_ptr call sites, onyxd_if.c:186,390). */

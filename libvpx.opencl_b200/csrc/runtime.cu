@@ -24,6 +24,7 @@ static std::atomic<uint64_t> g_h2d_bytes{0}, g_d2h_bytes{0}, g_launches{0}, g_fr
 struct ProfSpan { int kind; cudaEvent_t a, b; };
 
 #define NSLOT 3          /* pinned/device record slots: parse N+1 while N uploads / runs */
+#define MAX_SPANS 4096   /* profiling spans kept between two profile_read calls */
 #define NBJOB 4          /* job-array ring for batched launches */
 
 struct Slot {
@@ -71,8 +72,13 @@ struct vp8b200_ctx {
     int bjobs_cap, bjobs_cur;
     uint64_t launches;
     bool blocking_sync;            /* VP8B200_SYNC=block: sleep instead of spinning in fetch */
-    cudaEvent_t fetch_done;
-    bool profiling;
+    /* lazy device->host fetch: the copy is queued on its own stream behind
+     * recon_done (recorded on the launch stream), fetch_done fires when the pixels are in host
+     * memory.  fetch_fb >= 0 while a copy may still be reading that device buffer. */
+    cudaStream_t copy_stream;
+    cudaEvent_t recon_done, fetch_done;
+    int fetch_fb;
+    bool profiling, prof_skip;
     std::vector<ProfSpan> *spans;
     /* cross-stream ordering between a context's own stream and a batch leader's stream */
     cudaEvent_t own_ev;            /* recorded on this context's stream when a batch must wait for it */
@@ -125,6 +131,13 @@ extern "C" void *vp8b200_host_alloc(size_t bytes)
     if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return NULL; }
     return p;
 }
+extern "C" void *vp8b200_host_alloc_on(int device, size_t bytes)
+{
+    /* the first CUDA call of a thread creates a primary context on the current device: select
+     * the decoder's device first, or every rank's frame buffers pin through GPU 0 */
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return NULL; }
+    return vp8b200_host_alloc(bytes);
+}
 extern "C" void vp8b200_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 /* Live contexts.  A batch member borrows an event owned by its leader (batch_ev = the
@@ -138,6 +151,7 @@ static void free_ctx(vp8b200_ctx *c)
     cudaSetDevice(c->device);
     if (c->batch_pending) cudaEventSynchronize(c->batch_ev);   /* a batch on another leader's stream may still use us */
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     {
         /* every batch this context led has finished now: members need not (and, once the
          * events below are destroyed, must not) wait for them any more */
@@ -163,6 +177,8 @@ static void free_ctx(vp8b200_ctx *c)
     cudaFree(c->d_imsg); cudaFree(c->d_diag); cudaFree(c->d_tickets); cudaFree(c->d_lfmsg);
     free(c->diag_tmp);
     if (c->fetch_done) cudaEventDestroy(c->fetch_done);
+    if (c->recon_done) cudaEventDestroy(c->recon_done);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->spans) {
         for (auto &sp : *c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
         delete c->spans;
@@ -199,6 +215,9 @@ static int create_impl(vp8b200_ctx *c)
     const Geo &g = c->geo;
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CK(c, cudaEventCreateWithFlags(&c->recon_done, cudaEventDisableTiming));
+    c->fetch_fb = -1;
     vp8b200_upload_constants();
     vp8b200_upload_intra_constants();
     CK(c, cudaGetLastError());
@@ -312,11 +331,29 @@ static int join_batch(vp8b200_ctx *c)
     return VP8B200_OK;
 }
 
+/* A copy queued by fetch_begin may still be reading device buffer `fb`: order work that will
+ * WRITE that buffer (on stream `s`) behind it.  Reads need no ordering. */
+static int order_after_fetch(vp8b200_ctx *c, cudaStream_t s, int fb)
+{
+    if (c->fetch_fb >= 0 && c->fetch_fb == fb) {
+        CK(c, cudaStreamWaitEvent(s, c->fetch_done, 0));
+        c->fetch_fb = -1;
+    }
+    return VP8B200_OK;
+}
+
 static bool hdr_ok(const vp8b200_ctx *c, const vp8b200_frame_hdr *h)
 {
-    return h->fb_new < c->n_fb && h->fb_last < c->n_fb && h->fb_golden < c->n_fb &&
-           h->fb_altref < c->n_fb && h->frame_type <= 1 && h->filter_level <= 63 &&
-           h->sharpness_level <= 7;
+    if (!(h->fb_new < c->n_fb && h->fb_last < c->n_fb && h->fb_golden < c->n_fb &&
+          h->fb_altref < c->n_fb && h->frame_type <= 1 && h->filter_type <= 1 &&
+          h->filter_level <= 63 && h->sharpness_level <= 7))
+        return false;
+    /* an inter frame is never reconstructed into one of its own references (the reference's
+     * get_free_fb, onyxd_if.c:242-259, only hands out buffers nobody refers to): k_inter would
+     * read the buffer it is writing */
+    if (h->frame_type == 1 && (h->fb_new == h->fb_last || h->fb_new == h->fb_golden || h->fb_new == h->fb_altref))
+        return false;
+    return true;
 }
 
 extern "C" int vp8b200_frame_begin(vp8b200_ctx *c, const vp8b200_frame_hdr *hdr, vp8b200_frame_bufs *bufs)
@@ -366,6 +403,10 @@ static bool scan_records(const Geo &g, const vp8b200_mb *mb, const vp8b200_aux *
             if (key && !intra) return false;
             const bool has_aux = m->y_mode == VP8B200_B_PRED || m->y_mode == VP8B200_SPLITMV;
             if (has_aux && m->u.aux >= n_aux) return false;
+            if (m->y_mode == VP8B200_B_PRED) {             /* k_intra indexes its predictor table with these */
+                const uint8_t *bm = aux[m->u.aux].b_mode;
+                for (int k = 0; k < 16; k++) if (bm[k] > VP8B200_B_HU_PRED) return false;
+            }
             if (intra) {
                 if (!key) cnt[col + 2 * row + 1]++;
                 n_intra++;
@@ -424,11 +465,13 @@ static void prof_mark(vp8b200_ctx *c, int kind, bool begin)
 {
     if (!c->profiling) return;
     if (begin) {
+        if (c->spans->size() >= MAX_SPANS) { c->prof_skip = true; return; }   /* nobody reads: stop collecting */
+        c->prof_skip = false;
         ProfSpan sp; sp.kind = kind;
         cudaEventCreate(&sp.a); cudaEventCreate(&sp.b);
         cudaEventRecord(sp.a, c->stream);
         c->spans->push_back(sp);
-    } else {
+    } else if (!c->prof_skip) {
         cudaEventRecord(c->spans->back().b, c->stream);
     }
 }
@@ -476,6 +519,7 @@ extern "C" int vp8b200_frame_submit(vp8b200_ctx *c, uint32_t n_aux, uint32_t n_c
     c->own_dirty = true;
     Slot &s = c->slot[c->cur];
     const vp8b200_frame_hdr &h = c->cur_hdr;
+    { int os = order_after_fetch(c, c->stream, h.fb_new); if (os) return os; }
     const bool key = h.frame_type == 0;
     /* key frames use the context's static wavefront order; P frames list their intra MBs */
     unsigned n_intra = 0, n_split = 0;
@@ -500,18 +544,67 @@ extern "C" int vp8b200_frame_submit(vp8b200_ctx *c, uint32_t n_aux, uint32_t n_c
     return st;
 }
 
+/* SURVEY 8f N2 / N3.  display_w == 0: the whole allocation (borders included); otherwise only
+ * what a caller of vpx_codec_get_frame can see - display_w x display_h luma and
+ * ((w+1)/2) x ((h+1)/2) chroma samples (vpxdec.c:1093-1115) - as three pitched copies that land
+ * at the same offsets as in the device buffer, so img->planes[] / stride[] of the host mirror
+ * stay valid (vp8_dx_iface.c:319-348). */
+extern "C" int vp8b200_frame_fetch_begin(vp8b200_ctx *c, int fb, uint8_t *dst, int display_w, int display_h)
+{
+    if (!c || fb < 0 || fb >= c->n_fb || !dst || display_w < 0 || display_h < 0 ||
+        display_w > c->geo.width || display_h > c->geo.height || (display_w == 0) != (display_h == 0))
+        return VP8B200_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    { int js = join_batch(c); if (js) return js; }
+    if (c->fetch_fb >= 0) {
+        /* one copy is tracked per context: the previous one was never waited for (the caller
+         * skipped vpx_codec_get_frame).  Later launches simply wait for it. */
+        CK(c, cudaStreamWaitEvent(c->stream, c->fetch_done, 0));
+        c->fetch_fb = -1;
+    }
+    const Geo &g = c->geo;
+    CK(c, cudaEventRecord(c->recon_done, c->stream));
+    CK(c, cudaStreamWaitEvent(c->copy_stream, c->recon_done, 0));
+    if (display_w == 0) {
+        CK(c, cudaMemcpyAsync(dst, c->fb[fb], c->frame_size, cudaMemcpyDeviceToHost, c->copy_stream));
+        g_d2h_bytes += c->frame_size;
+    } else {
+        const int cw = (display_w + 1) >> 1, ch = (display_h + 1) >> 1;
+        CK(c, cudaMemcpy2DAsync(dst + g.y_off, (size_t)g.y_stride, c->fb[fb] + g.y_off, (size_t)g.y_stride,
+                                (size_t)display_w, (size_t)display_h, cudaMemcpyDeviceToHost, c->copy_stream));
+        CK(c, cudaMemcpy2DAsync(dst + g.u_off, (size_t)g.uv_stride, c->fb[fb] + g.u_off, (size_t)g.uv_stride,
+                                (size_t)cw, (size_t)ch, cudaMemcpyDeviceToHost, c->copy_stream));
+        CK(c, cudaMemcpy2DAsync(dst + g.v_off, (size_t)g.uv_stride, c->fb[fb] + g.v_off, (size_t)g.uv_stride,
+                                (size_t)cw, (size_t)ch, cudaMemcpyDeviceToHost, c->copy_stream));
+        g_d2h_bytes += (uint64_t)display_w * display_h + 2ull * cw * ch;
+    }
+    CK(c, cudaEventRecord(c->fetch_done, c->copy_stream));
+    c->fetch_fb = fb;
+    return VP8B200_OK;
+}
+
+/* Wait until the copy queued by the last fetch_begin is in host memory.  Device faults of the
+ * frame's kernels surface here (or at the next call) as VP8B200_ERR_CUDA. */
+extern "C" int vp8b200_frame_fetch_wait(vp8b200_ctx *c)
+{
+    if (!c) return VP8B200_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaEventSynchronize(c->fetch_done));
+    c->fetch_fb = -1;
+    return VP8B200_OK;
+}
+
 extern "C" int vp8b200_frame_fetch(vp8b200_ctx *c, int fb, uint8_t *dst, size_t bytes)
 {
     if (!c || fb < 0 || fb >= c->n_fb || !dst || bytes > c->frame_size) return VP8B200_ERR_INVALID;
+    if (bytes == c->frame_size) {
+        int st = vp8b200_frame_fetch_begin(c, fb, dst, 0, 0);
+        return st ? st : vp8b200_frame_fetch_wait(c);
+    }
     CK(c, cudaSetDevice(c->device));
     { int js = join_batch(c); if (js) return js; }
     CK(c, cudaMemcpyAsync(dst, c->fb[fb], bytes, cudaMemcpyDeviceToHost, c->stream));
-    if (c->blocking_sync) {
-        CK(c, cudaEventRecord(c->fetch_done, c->stream));
-        CK(c, cudaEventSynchronize(c->fetch_done));
-    } else {
-        CK(c, cudaStreamSynchronize(c->stream));
-    }
+    CK(c, cudaStreamSynchronize(c->stream));
     g_d2h_bytes += bytes;
     return VP8B200_OK;
 }
@@ -521,6 +614,8 @@ extern "C" int vp8b200_frame_upload(vp8b200_ctx *c, int fb, const uint8_t *src, 
     if (!c || fb < 0 || fb >= c->n_fb || !src || bytes > c->frame_size) return VP8B200_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     { int js = join_batch(c); if (js) return js; }
+    { int os = order_after_fetch(c, c->stream, fb); if (os) return os; }
+    c->own_dirty = true;
     CK(c, cudaMemcpyAsync(c->fb[fb], src, bytes, cudaMemcpyHostToDevice, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return VP8B200_OK;
@@ -532,6 +627,7 @@ extern "C" int vp8b200_frame_copy(vp8b200_ctx *c, int fb_dst, int fb_src)
     if (fb_dst == fb_src) return VP8B200_OK;
     CK(c, cudaSetDevice(c->device));
     { int js = join_batch(c); if (js) return js; }
+    { int os = order_after_fetch(c, c->stream, fb_dst); if (os) return os; }
     c->own_dirty = true;
     CK(c, cudaMemcpyAsync(c->fb[fb_dst], c->fb[fb_src], c->frame_size, cudaMemcpyDeviceToDevice, c->stream));
     return VP8B200_OK;
@@ -543,7 +639,9 @@ extern "C" int vp8b200_sync(vp8b200_ctx *c)
     CK(c, cudaSetDevice(c->device));
     { int js = join_batch(c); if (js) return js; }
     CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, cudaStreamSynchronize(c->copy_stream));
     c->own_dirty = false;
+    c->fetch_fb = -1;
     return VP8B200_OK;
 }
 
@@ -640,10 +738,12 @@ extern "C" int vp8b200_batch_run(vp8b200_ctx *const *ctx, vp8b200_staged *const 
     /* order the batch after whatever the members queued on their own streams, and after the
      * batch (possibly under another leader) that last touched them */
     { int js = join_batch(c); if (js) return js; }
+    { int os = order_after_fetch(c, c->stream, frame[0]->hdr.fb_new); if (os) return os; }
     for (int i = 1; i < n; i++) {
         vp8b200_ctx *m = ctx[i];
         if (m->batch_pending && m->batch_leader != c)       /* same leader = same stream: already ordered */
             CK(c, cudaStreamWaitEvent(c->stream, m->batch_ev, 0));
+        { int os = order_after_fetch(m, c->stream, frame[i]->hdr.fb_new); if (os) return os; }
         if (m->own_dirty) {
             CK(c, cudaEventRecord(m->own_ev, m->stream));
             CK(c, cudaStreamWaitEvent(c->stream, m->own_ev, 0));
@@ -672,6 +772,9 @@ extern "C" int vp8b200_batch_run(vp8b200_ctx *const *ctx, vp8b200_staged *const 
     int st = run_jobs(c, c->d_bjobs[r], n, any_inter, any_split, max_intra, any_lf);
     if (st) return st;
     CK(c, cudaEventRecord(c->lead_ev[r], c->stream));
+    /* the leader's own buffers were written on its own stream: if it later joins a batch under
+     * another leader, that batch has to wait for this one */
+    c->own_dirty = true;
     for (int i = 1; i < n; i++) { ctx[i]->batch_ev = c->lead_ev[r]; ctx[i]->batch_pending = true; ctx[i]->batch_leader = c; }
     return VP8B200_OK;
 }

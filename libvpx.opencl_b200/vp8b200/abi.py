@@ -15,7 +15,8 @@ LIB_PATH = os.environ.get("VP8B200_LIB") or os.path.join(os.path.dirname(_HERE),
 EXPORTS = [
     "vp8b200_abi_version", "vp8b200_strerror", "vp8b200_last_error", "vp8b200_device_count",
     "vp8b200_create", "vp8b200_destroy", "vp8b200_frame_size", "vp8b200_y_stride",
-    "vp8b200_host_alloc", "vp8b200_host_free", "vp8b200_frame_begin", "vp8b200_frame_submit",
+    "vp8b200_host_alloc", "vp8b200_host_alloc_on", "vp8b200_host_free", "vp8b200_frame_fetch_begin",
+    "vp8b200_frame_fetch_wait", "vp8b200_frame_begin", "vp8b200_frame_submit",
     "vp8b200_frame_abort", "vp8b200_frame_fetch", "vp8b200_frame_upload", "vp8b200_frame_copy",
     "vp8b200_sync", "vp8b200_stage_frame", "vp8b200_staged_free", "vp8b200_batch_run",
     "vp8b200_launch_count", "vp8b200_stream", "vp8b200_global_stats", "vp8b200_profile_enable",
@@ -52,6 +53,10 @@ def lib():
         L.vp8b200_frame_submit.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
         L.vp8b200_frame_abort.argtypes = [C.c_void_p]
         L.vp8b200_frame_fetch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+        L.vp8b200_frame_fetch_begin.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        L.vp8b200_frame_fetch_wait.argtypes = [C.c_void_p]
+        L.vp8b200_host_alloc_on.restype = C.c_void_p
+        L.vp8b200_host_alloc_on.argtypes = [C.c_int, C.c_size_t]
         L.vp8b200_frame_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
         L.vp8b200_frame_copy.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.vp8b200_sync.argtypes = [C.c_void_p]
@@ -128,6 +133,15 @@ class Context:
         if out is None:
             out = np.empty(self.frame_size, np.uint8)
         self._ck(self.L.vp8b200_frame_fetch(self.h, fb, out.ctypes.data_as(C.c_void_p), out.size), "frame_fetch")
+        return out
+
+    def fetch_visible(self, fb, display_w, display_h, out=None):
+        """Lazy fetch of the visible samples only; the rest of `out` is left untouched."""
+        if out is None:
+            out = np.zeros(self.frame_size, np.uint8)
+        self._ck(self.L.vp8b200_frame_fetch_begin(self.h, fb, out.ctypes.data_as(C.c_void_p), display_w, display_h),
+                 "frame_fetch_begin")
+        self._ck(self.L.vp8b200_frame_fetch_wait(self.h), "frame_fetch_wait")
         return out
 
     def upload(self, fb, buf):

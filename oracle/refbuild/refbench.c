@@ -103,6 +103,7 @@ int main(int argc, char **argv)
     int go[2], done[2];
     double t0, t1;
     long total = 0;
+    uint64_t checksum = 0;
 
     for (i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--procs") && i + 1 < argc) procs = atoi(argv[++i]);
@@ -128,20 +129,25 @@ int main(int argc, char **argv)
             if (read(go[0], &c, 1) < 0) _exit(3);      /* wait for the start signal (EOF) */
             for (r = 0; r < repeat; r++)
                 for (i = w; i < nfiles; i += procs) n += decode_stream(&blobs[i], touch, &sum);
-            if (write(done[1], &n, sizeof n) != sizeof n) _exit(3);
-            _exit(sum == 0xdeadbeefULL ? 4 : 0);
+            {
+                uint64_t msg[2];
+                msg[0] = (uint64_t)n; msg[1] = sum;
+                if (write(done[1], msg, sizeof msg) != sizeof msg) _exit(3);
+            }
+            _exit(0);
         }
     }
     close(go[0]);
     t0 = now_s();
     close(go[1]);                      /* releases every worker at once */
     for (w = 0; w < procs; w++) {
-        long n = 0;
-        if (read(done[0], &n, sizeof n) == sizeof n) total += n;
+        uint64_t msg[2] = {0, 0};
+        if (read(done[0], msg, sizeof msg) == sizeof msg) { total += (long)msg[0]; checksum += msg[1]; }
     }
     t1 = now_s();
     for (w = 0; w < procs; w++) { int st; wait(&st); if (!WIFEXITED(st) || WEXITSTATUS(st)) { fprintf(stderr, "worker failed\n"); return 1; } }
-    printf("{\"frames\": %ld, \"wall_s\": %.6f, \"fps\": %.3f, \"procs\": %d, \"streams\": %d, \"repeat\": %d}\n",
-           total, t1 - t0, total / (t1 - t0), procs, nfiles, repeat);
+    printf("{\"frames\": %ld, \"wall_s\": %.6f, \"fps\": %.3f, \"procs\": %d, \"streams\": %d, \"repeat\": %d, "
+           "\"touch\": %d, \"checksum\": %llu}\n",
+           total, t1 - t0, total / (t1 - t0), procs, nfiles, repeat, touch, (unsigned long long)checksum);
     return 0;
 }

@@ -29,6 +29,34 @@ def test_upload_fetch_copy_roundtrip(gpu_lib):
     ctx.close()
 
 
+def test_lazy_fetch_of_the_visible_samples(gpu_lib):
+    """N2/N3: fetch_begin queues the copy, fetch_wait delivers it; with a display size only the
+    visible luma / chroma samples move and every other byte of the host image stays as it was."""
+    geo = frames.Geometry(64, 48)
+    ctx = abi.Context(64, 48, 4)
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 256, geo.frame_size, dtype=np.uint8)
+    ctx.upload(1, a)
+    dw, dh = 61, 43                                               # odd display size: chroma is (w+1)/2 x (h+1)/2
+    out = ctx.fetch_visible(1, dw, dh, np.full(geo.frame_size, 0xEE, np.uint8))
+    assert np.array_equal(geo.i420(out, dw, dh), geo.i420(a, dw, dh))
+    want = np.full(geo.frame_size, 0xEE, np.uint8)
+    for off, stride, w, h in ((geo.y_off, geo.y_stride, dw, dh), (geo.u_off, geo.uv_stride, (dw + 1) // 2, (dh + 1) // 2),
+                              (geo.v_off, geo.uv_stride, (dw + 1) // 2, (dh + 1) // 2)):
+        for y in range(h):
+            want[off + y * stride: off + y * stride + w] = a[off + y * stride: off + y * stride + w]
+    assert np.array_equal(out, want)
+    # whole allocation through the same lazy pair; a second begin before the wait is legal
+    buf1, buf2 = np.zeros(geo.frame_size, np.uint8), np.zeros(geo.frame_size, np.uint8)
+    assert gpu_lib.vp8b200_frame_fetch_begin(ctx.h, 1, buf1.ctypes.data_as(C.c_void_p), 0, 0) == 0
+    assert gpu_lib.vp8b200_frame_fetch_begin(ctx.h, 1, buf2.ctypes.data_as(C.c_void_p), 0, 0) == 0
+    assert gpu_lib.vp8b200_frame_fetch_wait(ctx.h) == 0
+    assert np.array_equal(buf1, a) and np.array_equal(buf2, a)
+    assert gpu_lib.vp8b200_frame_fetch_begin(ctx.h, 1, buf1.ctypes.data_as(C.c_void_p), 65, 48) == -1   # wider than coded
+    assert gpu_lib.vp8b200_frame_fetch_begin(ctx.h, 1, buf1.ctypes.data_as(C.c_void_p), 64, 0) == -1
+    ctx.close()
+
+
 def test_invalid_records_are_rejected_not_executed(gpu_lib):
     """A corrupt record must come back as an error code, never as a wild device read."""
     mb_cols, mb_rows = 6, 4
@@ -60,6 +88,19 @@ def test_invalid_records_are_rejected_not_executed(gpu_lib):
     bad = recfile.Frame(good.hdr.copy(), good.mb.copy(), good.aux.copy(), good.coef.copy(), 1, 0)
     bad.mb["y_mode"][0] = 9                                       # SPLITMV pointing at a missing aux entry
     bad.mb["mv_row"][0], bad.mb["mv_col"][0] = np.array([12345], "<u4").view("<i2")
+    assert submit(bad) == -1
+    bad = recfile.Frame(good.hdr.copy(), good.mb.copy(), good.aux.copy(), good.coef.copy(), 1, 0)
+    bad.hdr["filter_type"] = 2
+    assert submit(bad) == -1
+    bad = recfile.Frame(good.hdr.copy(), good.mb.copy(), good.aux.copy(), good.coef.copy(), 1, 0)
+    bad.hdr["fb_new"] = bad.hdr["fb_golden"]                       # an inter frame written into its own reference
+    assert submit(bad) == -1
+    key = randrec.random_frame(rng, mb_cols, mb_rows, key=True)
+    assert submit(key) == 0
+    bpred = np.flatnonzero(key.mb["y_mode"] == 4)
+    assert bpred.size
+    bad = recfile.Frame(key.hdr.copy(), key.mb.copy(), key.aux.copy(), key.coef.copy(), 1, 0)
+    bad.aux[int(np.array([bad.mb["mv_row"][bpred[0]], bad.mb["mv_col"][bpred[0]]], "<i2").view("<u4")[0])][7] = 10   # sub-block mode out of range
     assert submit(bad) == -1
     assert gpu_lib.vp8b200_frame_submit(ctx.h, 0, 0) == -1        # submit without begin
     assert submit(good) == 0                                      # the context stays usable

@@ -42,3 +42,59 @@ def test_multi_stream_driver_runs(gpu_lib):
     r = json.loads(out.stdout.strip().splitlines()[-1])
     assert r["frames"] == 2 * 3 * (30 + 30) and r["checksum"] > 0 and r["kernel_launches"] > 0
     assert r["h2d_bytes"] > 0 and r["d2h_bytes"] > 0
+
+
+def _bench(*args, clips=("cif_p0.ivf", "qcif_arf.ivf"), env=None):
+    import json
+    exe = os.path.join(ROOT, "hostdec", "_build", "b200bench")
+    out = subprocess.run([exe] + list(args) + [os.path.join(GOLD, c) for c in clips], env=env,
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def test_lazy_fetch_pipeline_and_frame_delay_deliver_the_same_pixels(gpu_lib):
+    """SURVEY 8f N2.  The device wait sits in vpx_codec_get_frame: a worker that collects a frame
+    only after parsing its other streams (--pipeline), and the opt-in one-frame-delay mode with
+    decode(NULL, 0) as flush (--delay), must deliver byte for byte the pictures of the blocking
+    call order - and of the unmodified reference decoder (refbench --touch sums the same
+    visible pixels)."""
+    base = _bench("--threads", "2", "--streams", "4", "--repeat", "2", "--touch")
+    assert base["frames"] == 2 * 2 * (30 + 30) and base["touch"] == 1
+    pipe = _bench("--threads", "2", "--streams", "4", "--repeat", "2", "--touch", "--pipeline")
+    delay = _bench("--threads", "2", "--streams", "4", "--repeat", "2", "--touch", "--delay")
+    one = _bench("--threads", "1", "--streams", "4", "--repeat", "2", "--touch", "--delay", "--pipeline")
+    for r in (pipe, delay, one):
+        assert r["frames"] == base["frames"] and r["checksum"] == base["checksum"]
+    assert delay["frame_delay"] == 1 and pipe["pipeline"] == 1
+    full = _bench("--threads", "2", "--streams", "4", "--repeat", "2", "--touch", env=dict(os.environ, VP8B200_FETCH="full"))
+    assert full["checksum"] == base["checksum"] and full["d2h_bytes"] > base["d2h_bytes"]
+    # visible samples only: 1.5 * W * H bytes per shown frame (N3)
+    per_pass = 30 * (352 * 288 * 3 // 2) + 30 * (176 * 144 * 3 // 2)
+    assert abs(base["d2h_bytes"] - 2 * 2 * per_pass) <= 0.02 * 2 * 2 * per_pass
+    refbench = os.path.join(ROOT, "oracle", "_ref", "refbench")
+    if os.path.exists(refbench):
+        import json
+        out = subprocess.run([refbench, "--procs", "2", "--repeat", "2", "--touch",
+                              os.path.join(GOLD, "cif_p0.ivf"), os.path.join(GOLD, "qcif_arf.ivf")],
+                             stdout=subprocess.PIPE, text=True, timeout=300)
+        ref = json.loads(out.stdout.strip().splitlines()[-1])
+        assert ref["frames"] * 2 == base["frames"] and ref["checksum"] * 2 == base["checksum"]
+
+
+@pytest.mark.parametrize("name", ["cif_p0", "qcif_arf", "qcif_p1"])
+def test_set_and_copy_reference_match_the_reference_decoder(gpu_lib, name):
+    """VP8_COPY_REFERENCE / VP8_SET_REFERENCE (onyxd_if.c:161-230) through the public
+    API.  hostdec/reftest.c is built against the unmodified reference (oracle/_ref/reftest_ref)
+    and against the B200 host decoder; everything a caller can observe must be identical."""
+    a = os.path.join(ROOT, "oracle", "_ref", "reftest_ref")
+    b = os.path.join(ROOT, "hostdec", "_build", "reftest_b200")
+    assert os.path.exists(b), "hostdec is not built"
+    if not os.path.exists(a):
+        pytest.skip("oracle/_ref not built")
+    clip = os.path.join(GOLD, name + ".ivf")
+    want = subprocess.run([a, clip], stdout=subprocess.PIPE, text=True, timeout=300)
+    got = subprocess.run([b, clip], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert want.returncode == 0 and got.returncode == 0, got.stderr[-400:]
+    assert "set last: ok" in want.stdout and want.stdout.count("shown") == 8 or name == "qcif_arf"
+    assert got.stdout == want.stdout
