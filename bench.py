@@ -40,6 +40,22 @@ REFDIR = os.path.join(ROOT, "oracle", "_ref")
 METRIC = "decode_fps_1080p_64streams_md5_exact"
 
 
+def workload_config(S, F, n_clips):
+    """The workload description, identical in both arms (our arm adds its own launch layout
+    under "impl_config")."""
+    return {"workload": "c5_64x1080p", "streams_per_gpu": S, "frames_per_clip": F, "unique_clips": n_clips,
+            "resolution": "1920x1080 (coded 1920x1088)", "profile": 0, "loop_filter": "normal", "mc": "sixtap",
+            "step": "one frame of each of the %d streams" % S,
+            "consumer": "every visible pixel of every output frame is read (byte sum), both arms",
+            "l2_policy": "inputs per step (~%.0f MB) exceed the 126 MB L2" % (S * 3 * 3428352 / 1e6)}
+
+
+def assembler_found():
+    """the reference's x86 SIMD build needs yasm or nasm; say whether the box has one."""
+    import shutil
+    return {"yasm": bool(shutil.which("yasm")), "nasm": bool(shutil.which("nasm"))}
+
+
 def find_clips():
     clips = sorted(glob.glob(os.path.join(STREAMS, "c5_1080p_s*.ivf")))
     if not clips and os.path.exists(os.path.join(REFDIR, "vpxenc")):
@@ -259,6 +275,20 @@ def run_b200(args):
     tot_ms = sum(v[0] for v in prof.values()) or 1.0
     for k in kern:
         kern[k]["share"] = round(prof[k][0] / tot_ms, 4)
+    border_bytes = F * S * (geo.frame_size - 1.5 * na)
+    kern["border"]["GBps"] = round(border_bytes / (prof["border"][0] / 1e3) / 1e9, 1) if prof["border"][0] else None
+    if kern["border"]["GBps"]:
+        kern["border"]["frac"] = round(kern["border"]["GBps"] / peak, 4)
+    # inter: reference read + destination write of the inter macroblocks + the records; intra: destination write
+    n_inter = sum(int((recs[mine[s]].frames[f].mb["ref_frame"] != 0).sum()) for f in range(F) for s in range(S))
+    n_intra = F * S * (na // 256) - n_inter
+    rec_bytes = sum(16 * recs[mine[s]].frames[f].mb.shape[0] + 64 * recs[mine[s]].frames[f].n_aux + 32 * recs[mine[s]].frames[f].n_coef
+                    for f in range(F) for s in range(S))
+    share = n_inter / max(n_inter + n_intra, 1)
+    for k, b in (("inter", n_inter * 768 + rec_bytes * share), ("intra", n_intra * 384 + rec_bytes * (1 - share))):
+        if prof[k][0]:
+            kern[k]["GBps"] = round(b / (prof[k][0] / 1e3) / 1e9, 1)
+            kern[k]["frac"] = round(kern[k]["GBps"] / peak, 4)
     pred_ms = prof["inter"][0] + prof["intra"][0]
     kern["pred_GBps"] = round(pred_bytes / (pred_ms / 1e3) / 1e9, 1) if pred_ms else None
     achieved = lf_bytes / (lf_ms / 1e3) / 1e9 if lf_ms else 0.0
@@ -283,21 +313,24 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = run_refbench(clips, sample_streams=min(len(clips), os.cpu_count() or 1), repeat=1)
 
+    extra = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        extra = north_star_extras(clips, local_rank, measured_peak()[0])
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": round(tot_s * 1e3 / K, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "c5_64x1080p", "streams_per_gpu": S, "frames_per_clip": F, "stream_groups": G,
-                       "group_phase_offsets_frames": off,
-                       "unique_clips": len(clips), "resolution": "1920x1080 (coded 1920x1088)",
-                       "profile": 0, "loop_filter": "normal", "mc": "sixtap",
-                       "step": "one frame of each of the %d streams (one batched launch per kernel and stream group)" % S,
-                       "l2_policy": "inputs per step (~%.0f MB) exceed the 126 MB L2" % (S * 3 * geo.frame_size / 1e6),
-                       "pixels_per_s": round(value * 1920 * 1080), "md5_checked_frames": checked,
-                       "setup_s": round(t_setup, 1)},
+            "config": workload_config(S, F, len(clips)),
+            "impl_config": {"stream_groups": G, "group_phase_offsets_frames": off,
+                            "launches": "one batched launch per kernel, step and stream group",
+                            "md5_checked_frames": checked, "setup_s": round(t_setup, 1)},
+            "pixels_per_s": round(value * 1920 * 1080),
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
         }
+        if extra:
+            line["north_star"] = extra
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -310,7 +343,8 @@ def run_e2e(args, clips, mine, local_rank, dist, dev, shard, S):
     repeat = max(1, args.e2e_repeat)
     env = dict(os.environ, VP8B200_DEVICE=str(local_rank), VP8B200_SYNC="block")
     cmd = [os.path.join(HOSTDEC, "b200bench"), "--threads", str(threads), "--streams", str(S),
-           "--repeat", str(repeat)] + [clips[u] for u in mine]
+           "--repeat", str(repeat), "--touch"] + (["--pipeline"] if args.e2e_pipeline else []) + \
+          (["--delay"] if args.e2e_delay else []) + [clips[u] for u in mine]
     if dist is not None:
         dist.barrier()
     out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
@@ -322,7 +356,69 @@ def run_e2e(args, clips, mine, local_rank, dist, dev, shard, S):
     return {"value": round(frames_tot / wall, 2), "unit": "frames/s",
             "h2d_bytes_per_step": round(r["h2d_bytes"] * per_step), "d2h_bytes_per_step": round(r["d2h_bytes"] * per_step),
             "api": "vpx_codec_decode/vpx_codec_get_frame (hostdec/b200bench)", "host_threads": r["threads"],
-            "host_cores": os.cpu_count(), "frames": r["frames"], "wall_s": round(r["wall_s"], 3)}
+            "host_cores": os.cpu_count(), "frames": r["frames"], "wall_s": round(r["wall_s"], 3),
+            "touch": bool(r.get("touch")), "pipeline": bool(r.get("pipeline")), "frame_delay": bool(r.get("frame_delay")),
+            "checksum_per_pass": r["checksum"] // repeat if r.get("checksum") else None,
+            "kernel_launches_per_frame": round(r["kernel_launches"] / max(r["frames"], 1), 3),
+            "cpu_ms_per_frame": {"decode": r["cpu_ms_per_frame_decode"], "get_frame": r["cpu_ms_per_frame_get_frame"],
+                                 "blocked": r["blocked_ms_per_frame"]}}
+
+
+def _b200bench(args_list, env_extra=None):
+    env = dict(os.environ, VP8B200_SYNC="block")
+    env.update(env_extra or {})
+    out = subprocess.run([os.path.join(HOSTDEC, "b200bench")] + args_list, env=env, stdout=subprocess.PIPE,
+                         stderr=subprocess.PIPE, text=True)
+    if out.returncode != 0:
+        raise SystemExit("bench: b200bench failed: " + out.stderr[-400:])
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def north_star_extras(clips, local_rank, peak):
+    """Untimed extras the north star asks for next to the headline (rank 0, N = 1): single-stream
+    1080p / 2160p frames/s with the records resident and through the public API (blocking call
+    order and the opt-in frame-delay mode), the host parser's own ceiling on this box, and the
+    x86-assembler probe for the reference's SIMD build."""
+    from vp8b200 import abi, recfile
+    dev_env = {"VP8B200_DEVICE": str(local_rank)}
+    out = {"host_cores": os.cpu_count(), "assembler_on_box": assembler_found()}
+    streams = [("1080p", clips[0])]
+    c4 = os.path.join(STREAMS, "c4_2160p.ivf")
+    if os.path.exists(c4):
+        streams.append(("2160p_8partitions", c4))
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, ivf in streams:
+            rec = recfile.read(capture_records([ivf], tmp)[0])
+            F = len(rec.frames)
+            ctx = abi.Context(rec.coded_width, rec.coded_height, rec.n_fb, device=local_rank)
+            staged = [ctx.stage(fr) for fr in rec.frames]
+            ctx.profile(True)
+            best = None
+            for _ in range(3):
+                for f in range(F):
+                    abi.batch_run([ctx], [staged[f]])
+                prof = ctx.profile_read()
+                ms = sum(v[0] for v in prof.values())
+                if best is None or ms < best[0]:
+                    best = (ms, prof)
+            ctx.close()
+            na = rec.coded_width * rec.coded_height
+            lf_bytes = sum(frame_bytes_model(fr, na)["loopfilter"] for fr in rec.frames)
+            row = {"frames": F, "resident_fps": round(F / (best[0] * 1e-3), 1),
+                   "resident_pixels_per_s": round(F / (best[0] * 1e-3) * rec.display_width * rec.display_height),
+                   "kernel_ms_per_frame": {k: round(v[0] / F, 4) for k, v in best[1].items()},
+                   "loopfilter_frac_of_hbm": round(lf_bytes / (best[1]["loopfilter"][0] * 1e-3) / 1e9 / peak, 4) if best[1]["loopfilter"][0] else None}
+            r = _b200bench(["--threads", "1", "--streams", "1", "--repeat", "3", "--touch", ivf], dev_env)
+            row["e2e_fps_blocking_call_order"] = round(r["fps"], 1)
+            r = _b200bench(["--threads", "1", "--streams", "1", "--repeat", "3", "--touch", "--delay", ivf], dev_env)
+            row["e2e_fps_frame_delay_mode"] = round(r["fps"], 1)
+            r = _b200bench(["--threads", "1", "--streams", "1", "--repeat", "3", ivf], {"VP8B200_NO_DEVICE": "1"})
+            row["host_parse_only_fps"] = round(r["fps"], 1)
+            out[name] = row
+    cores = os.cpu_count() or 1
+    r = _b200bench(["--threads", str(cores), "--streams", "64", "--repeat", "2"] + clips[:64], {"VP8B200_NO_DEVICE": "1"})
+    out["host_parse_only_fps_all_cores_64_streams"] = round(r["fps"], 1)
+    return out
 
 
 def run_refbench(clips, sample_streams, repeat, procs=None):
@@ -334,39 +430,42 @@ def run_refbench(clips, sample_streams, repeat, procs=None):
     r = json.loads(out.stdout.strip().splitlines()[-1])
     return {"value": round(r["fps"], 2), "unit": "frames/s", "cores": r["procs"], "kind": "reference",
             "sample": "%d 1080p clips x %d pass(es) = %d frames, unmodified reference generic-C decoder, "
-                      "one process per core" % (sample_streams, repeat, r["frames"]),
+                      "one process per core, every output pixel read" % (sample_streams, repeat, r["frames"]),
+            "build": "generic C; x86 SIMD build needs yasm/nasm: %s" % json.dumps(assembler_found()),
             "wall_s": round(r["wall_s"], 3)}
 
 
 def run_reference(args):
-    """The reference's own CPU implementation of the path, all host cores, same config/metric."""
+    """The reference's own CPU implementation of the path, all host cores, same config/metric:
+    the UNMODIFIED reference decoder (oracle/_ref, generic C) decodes exactly --steps frames of
+    each of the 64 streams, one process per core, and reads every output pixel like our arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     clips = find_clips()
     S = args.streams
     use = [clips[i % len(clips)] for i in range(S)]
-    # K steps = K frames of each of the S streams; the clip has F frames -> ceil(K/F) passes
     F = len(open(use[0][:-4] + ".md5").read().split())
-    passes = max(1, -(-args.steps // F))
     procs = os.cpu_count() or 1
-    cmd = [os.path.join(REFDIR, "refbench"), "--procs", str(procs), "--repeat", str(passes), "--touch"] + use
+    base = [os.path.join(REFDIR, "refbench"), "--procs", str(procs), "--touch"]
     if args.warmup:
-        subprocess.run([os.path.join(REFDIR, "refbench"), "--procs", str(procs)] + use[:procs], stdout=subprocess.DEVNULL)
-    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        subprocess.run(base + ["--frames", str(args.warmup)] + use[:procs], stdout=subprocess.DEVNULL)
+    out = subprocess.run(base + ["--frames", str(args.steps)] + use, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     if out.returncode != 0:
         raise SystemExit("bench: refbench failed: " + out.stderr[-400:])
     r = json.loads(out.stdout.strip().splitlines()[-1])
     steps = r["frames"] / S
     cpu = {"value": round(r["fps"], 2), "unit": "frames/s", "cores": r["procs"], "kind": "reference",
-           "sample": "%d streams x %d pass(es) of %d frames, one process per core" % (S, passes, F)}
+           "build": "generic C (--target=generic-gnu equivalent, -O3), no assembler on the box: %s" % json.dumps(assembler_found()),
+           "sample": "%d streams x %d frames, one process per core, every output pixel read" % (S, args.steps)}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(r["fps"], 2), "unit": "frames/s",
-        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": int(steps), "warmup": args.warmup,
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": int(round(steps)), "warmup": args.warmup,
         "ms_per_step": round(r["wall_s"] * 1e3 / steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "c5_64x1080p", "streams_per_gpu": S, "frames_per_clip": F,
-                   "note": "CPU only: host cores do not scale with --gpus; rank 0 runs, others idle"},
+        "config": workload_config(S, F, len(clips)),
+        "impl_config": {"note": "CPU only: host cores do not scale with --gpus; rank 0 runs, others idle",
+                        "checksum": r.get("checksum")},
         "cpu_baseline": cpu,
         "e2e": {"value": round(r["fps"], 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -384,6 +483,10 @@ if __name__ == "__main__":
                     help="1: stream group g plays g*F/G frames ahead (streams out of phase); 0: all streams on the same frame")
     ap.add_argument("--e2e-threads", type=int, default=0)
     ap.add_argument("--e2e-repeat", type=int, default=4)
+    ap.add_argument("--e2e-pipeline", type=int, default=1,
+                    help="1: a worker collects a frame only after parsing its other streams (decode only queues device work)")
+    ap.add_argument("--e2e-delay", type=int, default=0, help="1: decoder frame-delay mode (VP8B200_FRAME_DELAY)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the untimed north-star extras (single-stream numbers)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: kernels only")
     ap.add_argument("--skip-verify", action="store_true", help="profiling runs: no MD5 pass")

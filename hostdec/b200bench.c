@@ -34,6 +34,7 @@
 #include "vpx/vpx_decoder.h"
 #include "vpx/vp8dx.h"
 #include "vp8b200.h"
+#include "bench_touch.h"
 
 typedef struct { uint8_t *data; size_t size; int nframes; size_t *off; uint32_t *len; } clip_t;
 typedef struct { vpx_codec_ctx_t dec; const clip_t *clip; int ready; } inst_t;
@@ -126,18 +127,7 @@ static long drain_one(inst_t *in, uint64_t *sum, double *cpu)
     while ((img = vpx_codec_get_frame(&in->dec, &it))) {
         shown++;
         if (sum) {
-            unsigned y, x;
-            uint64_t s = 0;
-            for (y = 0; y < img->d_h; y++) {
-                const uint8_t *r = img->planes[0] + (size_t)y * img->stride[0];
-                for (x = 0; x < img->d_w; x++) s += r[x];
-            }
-            for (y = 0; y < (img->d_h + 1) / 2; y++) {
-                const uint8_t *r1 = img->planes[1] + (size_t)y * img->stride[1];
-                const uint8_t *r2 = img->planes[2] + (size_t)y * img->stride[2];
-                for (x = 0; x < (img->d_w + 1) / 2; x++) s += r1[x] + r2[x];
-            }
-            *sum += s;
+            *sum += touch_image(img);
         } else {
             /* touch one byte per plane so the frame is really consumed from host memory */
             volatile uint8_t t = img->planes[0][0] ^ img->planes[1][0] ^ img->planes[2][0];

@@ -9,7 +9,10 @@
  * start signal to the last worker's exit, so the figure is whole-job aggregate
  * fps on P cores.
  *
- * usage: refbench [--procs P] [--repeat R] [--touch] a.ivf [b.ivf ...]
+ * usage: refbench [--procs P] [--repeat R] [--frames N] [--touch] a.ivf [b.ivf ...]
+ *   --frames N : decode exactly N frames of every stream (whole passes of the clip, then the
+ *             first N mod F frames of one more pass) instead of R whole passes - bench.py's
+ *             "--steps K" on the reference arm
  *   --touch : also read every visible output pixel (a checksum), the analogue
  *             of vpxdec writing/hashing the frame.
  * prints one JSON line.
@@ -24,6 +27,7 @@
 #include <sys/wait.h>
 #include "vpx/vpx_decoder.h"
 #include "vpx/vp8dx.h"
+#include "bench_touch.h"            /* hostdec/bench_touch.h: the same consumer as our arm */
 
 typedef struct { uint8_t *data; size_t size; } blob_t;
 
@@ -54,15 +58,15 @@ static double now_s(void)
 }
 
 /* decode one IVF blob; returns frames shown */
-static long decode_stream(const blob_t *b, int touch, uint64_t *sum)
+static long decode_stream(const blob_t *b, int touch, uint64_t *sum, long max_frames, long *decoded)
 {
     vpx_codec_ctx_t dec;
     vpx_codec_dec_cfg_t cfg = {0};
-    long shown = 0;
+    long shown = 0, frames_in = 0;
     size_t pos = 32;
     if (b->size < 32 || memcmp(b->data, "DKIF", 4)) { fprintf(stderr, "not IVF\n"); exit(2); }
     if (vpx_codec_dec_init(&dec, vpx_codec_vp8_dx(), &cfg, 0)) { fprintf(stderr, "init failed\n"); exit(2); }
-    while (pos + 12 <= b->size) {
+    while (pos + 12 <= b->size && (max_frames < 0 || frames_in < max_frames)) {
         uint32_t fsz = le32(b->data + pos);
         vpx_codec_iter_t it = NULL;
         vpx_image_t *img;
@@ -73,31 +77,21 @@ static long decode_stream(const blob_t *b, int touch, uint64_t *sum)
             exit(2);
         }
         pos += fsz;
+        frames_in++;
         while ((img = vpx_codec_get_frame(&dec, &it))) {
             shown++;
-            if (touch) {
-                unsigned y, x;
-                uint64_t s = 0;
-                for (y = 0; y < img->d_h; y++) {
-                    const uint8_t *r = img->planes[0] + (size_t)y * img->stride[0];
-                    for (x = 0; x < img->d_w; x++) s += r[x];
-                }
-                for (y = 0; y < (img->d_h + 1) / 2; y++) {
-                    const uint8_t *r1 = img->planes[1] + (size_t)y * img->stride[1];
-                    const uint8_t *r2 = img->planes[2] + (size_t)y * img->stride[2];
-                    for (x = 0; x < (img->d_w + 1) / 2; x++) s += r1[x] + r2[x];
-                }
-                *sum += s;
-            }
+            if (touch) *sum += touch_image(img);
         }
     }
     vpx_codec_destroy(&dec);
+    if (decoded) *decoded = frames_in;
     return shown;
 }
 
 int main(int argc, char **argv)
 {
     int procs = 1, repeat = 1, touch = 0, nfiles = 0, i, w;
+    long frames = -1;
     const char *files[4096];
     blob_t *blobs;
     int go[2], done[2];
@@ -109,6 +103,7 @@ int main(int argc, char **argv)
         if (!strcmp(argv[i], "--procs") && i + 1 < argc) procs = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--repeat") && i + 1 < argc) repeat = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--touch")) touch = 1;
+        else if (!strcmp(argv[i], "--frames") && i + 1 < argc) frames = atol(argv[++i]);
         else if (nfiles < 4096) files[nfiles++] = argv[i];
     }
     if (!nfiles) { fprintf(stderr, "usage: refbench [--procs P] [--repeat R] [--touch] a.ivf ...\n"); return 2; }
@@ -127,8 +122,20 @@ int main(int argc, char **argv)
             int r;
             close(go[1]);
             if (read(go[0], &c, 1) < 0) _exit(3);      /* wait for the start signal (EOF) */
-            for (r = 0; r < repeat; r++)
-                for (i = w; i < nfiles; i += procs) n += decode_stream(&blobs[i], touch, &sum);
+            if (frames < 0) {
+                for (r = 0; r < repeat; r++)
+                    for (i = w; i < nfiles; i += procs) n += decode_stream(&blobs[i], touch, &sum, -1, NULL);
+            } else {
+                for (i = w; i < nfiles; i += procs) {
+                    long left = frames;
+                    while (left > 0) {               /* whole passes, then a partial one */
+                        long in = 0;
+                        n += decode_stream(&blobs[i], touch, &sum, left, &in);
+                        if (in <= 0) break;
+                        left -= in;
+                    }
+                }
+            }
             {
                 uint64_t msg[2];
                 msg[0] = (uint64_t)n; msg[1] = sum;
