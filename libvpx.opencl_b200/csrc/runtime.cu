@@ -62,7 +62,7 @@ struct vp8b200_ctx {
     unsigned long long *d_imsg;    /* per-MB exported intra borders, 16 tagged words each */
     uint32_t *d_diag;              /* all MB indices sorted by wavefront index c + 2r */
     int *diag_tmp;                 /* host scratch for the counting sort */
-    uint8_t *d_lfmsg;              /* loop-filter row hand-off messages, 256 B per MB */
+    uint8_t *d_lfmsg;              /* loop-filter hand-off messages between CTAs (vp8b200_lf_msg_bytes) */
     unsigned *d_tickets;           /* [0] intra, [1] loop filter */
     unsigned ticket_base[2];
     unsigned epoch_intra, epoch_lf;
@@ -259,8 +259,8 @@ static int create_impl(vp8b200_ctx *c)
         free(tmp);
         CK(c, e);
     }
-    CK(c, cudaMalloc((void **)&c->d_lfmsg, (size_t)c->n_mb * 256));
-    CK(c, cudaMemsetAsync(c->d_lfmsg, 0, (size_t)c->n_mb * 256, c->stream));
+    CK(c, cudaMalloc((void **)&c->d_lfmsg, vp8b200_lf_msg_bytes(g)));
+    CK(c, cudaMemsetAsync(c->d_lfmsg, 0, vp8b200_lf_msg_bytes(g), c->stream));
     CK(c, cudaMalloc((void **)&c->d_tickets, 2 * sizeof(unsigned)));
     CK(c, cudaMemsetAsync(c->d_tickets, 0, 2 * sizeof(unsigned), c->stream));
     {

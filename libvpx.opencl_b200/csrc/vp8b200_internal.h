@@ -25,7 +25,7 @@ struct FrameJob {
     const int16_t *coef;
     unsigned long long *intra_msg; /* per-MB exported borders: 16 tagged 64-bit words          */
     const uint32_t *intra_list;   /* indices of the intra MBs, sorted by wavefront c + 2r     */
-    uint8_t *lf_msg;              /* loop-filter row hand-off: 256 B per macroblock           */
+    uint8_t *lf_msg;              /* loop-filter hand-off between CTAs: 512 B per macroblock of every LF_ROWS_PER_CTA-th row */
     unsigned int epoch_intra;     /* progress values of this frame are (epoch << 13) + columns; */
     unsigned int epoch_lf;        /* each counter advances only when its kernel really runs     */
     unsigned int n_intra;         /* intra macroblocks in the frame (0 => intra kernel idle)  */
@@ -46,6 +46,7 @@ void vp8b200_launch_intra(cudaStream_t s, const FrameJob *jobs, int n_jobs, cons
                           int *n_ctas);
 void vp8b200_launch_loopfilter(cudaStream_t s, const FrameJob *jobs, int n_jobs, const Geo &g,
                                unsigned int *ticket, unsigned int ticket_base, int *n_ctas);
+size_t vp8b200_lf_msg_bytes(const Geo &g);   /* size of FrameJob.lf_msg */
 void vp8b200_launch_border(cudaStream_t s, const FrameJob *jobs, int n_jobs, const Geo &g);
 
 #endif
