@@ -360,6 +360,8 @@ def run_e2e(args, clips, mine, local_rank, dist, dev, shard, S):
             "touch": bool(r.get("touch")), "pipeline": bool(r.get("pipeline")), "frame_delay": bool(r.get("frame_delay")),
             "checksum_per_pass": r["checksum"] // repeat if r.get("checksum") else None,
             "kernel_launches_per_frame": round(r["kernel_launches"] / max(r["frames"], 1), 3),
+            "coalescer": {"batches": r.get("engine_batches"), "frames": r.get("engine_frames"),
+                          "frames_per_batch": round(r["engine_frames"] / r["engine_batches"], 1) if r.get("engine_batches") else None},
             "cpu_ms_per_frame": {"decode": r["cpu_ms_per_frame_decode"], "get_frame": r["cpu_ms_per_frame_get_frame"],
                                  "blocked": r["blocked_ms_per_frame"]}}
 

@@ -209,7 +209,7 @@ int main(int argc, char **argv)
     int i;
     long total = 0;
     double tend = 0;
-    uint64_t st0[4], st1[4];
+    uint64_t st0[4], st1[4], eng[2] = {0, 0};
     double cpu_dec = 0, cpu_get = 0, runq = 0, thread_wall = 0;
     for (i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--threads") && i + 1 < argc) g_threads = atoi(argv[++i]);
@@ -243,6 +243,7 @@ int main(int argc, char **argv)
     vp8b200_global_stats(st0);
     for (i = 0; i < g_threads; i++) pthread_join(th[i], NULL);
     vp8b200_global_stats(st1);
+    vp8b200_engine_stats(getenv("VP8B200_DEVICE") ? atoi(getenv("VP8B200_DEVICE")) : 0, eng);
     for (i = 0; i < g_threads; i++) {
         total += g_frames[i]; cpu_dec += g_cpu_dec[i]; cpu_get += g_cpu_get[i];
         if (g_touch) g_checksum += g_tsum[i];
@@ -256,13 +257,13 @@ int main(int argc, char **argv)
                "\"repeat\": %d, \"h2d_bytes\": %.0f, \"d2h_bytes\": %.0f, \"kernel_launches\": %.0f, "
                "\"cpu_ms_per_frame_decode\": %.4f, \"cpu_ms_per_frame_get_frame\": %.4f, "
                "\"runq_wait_ms_per_frame\": %.4f, \"blocked_ms_per_frame\": %.4f, \"touch\": %d, \"pipeline\": %d, "
-               "\"frame_delay\": %d, \"checksum\": %llu}\n",
+               "\"frame_delay\": %d, \"engine_batches\": %llu, \"engine_frames\": %llu, \"checksum\": %llu}\n",
                total, tend - g_t0, total / (tend - g_t0), g_threads, g_streams, g_repeat,
                (double)(st1[0] - st0[0]) * share, (double)(st1[1] - st0[1]) * share,
                (double)(st1[2] - st0[2]) * share, 1e3 * cpu_dec / (total ? total : 1),
                1e3 * cpu_get / (total ? total : 1), 1e3 * runq / (total ? total : 1),
                1e3 * (thread_wall - cpu_dec - cpu_get - runq) / (total ? total : 1), g_touch, g_pipeline, g_delay,
-               (unsigned long long)g_checksum);
+               (unsigned long long)eng[0], (unsigned long long)eng[1], (unsigned long long)g_checksum);
     }
     return 0;
 }

@@ -35,6 +35,9 @@
  *   VP8B200_FRAME_DELAY=1  opt-in one-frame-delay mode: vpx_codec_get_frame after
  *                          decode(N) returns frame N-1, so the host parses frame N+1 while the
  *                          device reconstructs frame N; decode(NULL, 0) flushes the last frame
+ *   VP8B200_COALESCE=0     submit every frame on the decoder's own CUDA stream instead of handing
+ *                          it to the per-device engine that batches the frames of all decoder
+ *                          instances into one launch per kernel (default: 1, coalesce)
  *   VP8B200_FETCH=full     copy the whole allocation (borders included) instead of the visible
  *                          samples only
  *   VP8B200_NO_DEVICE=1    record-capture only: no device is touched and NO pixels are
@@ -98,6 +101,9 @@ typedef struct seam_state {
     vp8b200_mb *h_mb; vp8b200_aux *h_aux; int16_t *h_coef;
     /* lazy fetch: queued in vp8dx_get_raw_frame, waited for in vp8_get_frame */
     int fetch_full;               /* VP8B200_FETCH=full */
+    int coalesce;                 /* VP8B200_COALESCE (default 1): submit through the per-device engine */
+    int fetch_queued;             /* the engine was asked to copy the shown frame (frame_submit_show) */
+    uint8_t *fetch_queued_dst;
     int fetch_pending;            /* a fetch_begin nobody has waited for yet */
     int fetch_fb;                 /* its frame buffer index */
     int device_failed;            /* sticky: a device call failed, every later frame is an error */
@@ -139,6 +145,8 @@ static seam_state *seam_get(VP8D_COMP *pbi)
         s->frame_delay = e && atoi(e) && !s->no_device;
         e = getenv("VP8B200_FETCH");
         s->fetch_full = e && !strcmp(e, "full");
+        e = getenv("VP8B200_COALESCE");
+        s->coalesce = e ? atoi(e) != 0 : 1;
         e = getenv("VP8B200_DUMP");
         if (e && *e) {
             char path[1024];
@@ -689,6 +697,22 @@ void vp8b200_seam_record_mb(VP8D_COMP *pbi, MACROBLOCKD *xd, unsigned int mb_idx
     }
 }
 
+/* frame-delay mode: the two private pinned images pictures are copied to in turn */
+static uint8_t *seam_out_buffer(seam_state *s, size_t frame_size)
+{
+    uint8_t *out;
+    if (!s->out_buf[0] || s->out_size != frame_size) {
+        vp8b200_host_free(s->out_buf[0]); vp8b200_host_free(s->out_buf[1]);
+        s->out_buf[0] = (uint8_t *)vp8b200_host_alloc_on(seam_device(), frame_size);
+        s->out_buf[1] = (uint8_t *)vp8b200_host_alloc_on(seam_device(), frame_size);
+        s->out_size = frame_size;
+        if (!s->out_buf[0] || !s->out_buf[1]) return NULL;
+    }
+    out = s->out_buf[s->out_cur];
+    s->out_cur ^= 1;
+    return out;
+}
+
 static void seam_dump_frame(seam_state *s, VP8D_COMP *pbi, uint32_t n_mb)
 {
     VP8_COMMON *cm = &pbi->common;
@@ -718,7 +742,25 @@ void vp8b200_seam_frame_submit(VP8D_COMP *pbi)
         vpx_internal_error(&cm->error, VPX_CODEC_ERROR, "vp8b200: record arena overflow");
     if (s->dump) seam_dump_frame(s, pbi, (uint32_t)(cm->mb_rows * cm->mb_cols));
     s->open = 0;
-    if (s->ctx) {
+    s->fetch_queued = 0;
+    if (s->ctx && s->coalesce) {
+        /* hand the frame AND the request for its picture to the device's engine: this thread
+         * makes no CUDA launch (swap_frame_buffers has run: frame_to_show is this frame) */
+        int show_fb = -1;
+        uint8_t *dst = NULL;
+        if (cm->show_frame && cm->frame_to_show) {
+            show_fb = (int)(cm->frame_to_show - cm->yv12_fb);
+            dst = cm->frame_to_show->buffer_alloc;
+            if (s->frame_delay) {
+                dst = seam_out_buffer(s, (size_t)cm->frame_to_show->frame_size);
+                if (!dst) vpx_internal_error(&cm->error, VPX_CODEC_MEM_ERROR, "vp8b200: pinned output image");
+            }
+        }
+        st = vp8b200_frame_submit_show(s->ctx, s->cur.n_aux, s->cur.n_coef, show_fb, dst,
+                                       s->fetch_full ? 0 : cm->Width, s->fetch_full ? 0 : cm->Height);
+        if (st) seam_fail(pbi, "vp8b200_frame_submit_show", st);
+        if (show_fb >= 0) { s->fetch_queued = 1; s->fetch_queued_dst = dst; s->fetch_fb = show_fb; }
+    } else if (s->ctx) {
         st = vp8b200_frame_submit(s->ctx, s->cur.n_aux, s->cur.n_coef);
         if (st) seam_fail(pbi, "vp8b200_frame_submit", st);
     }
@@ -761,6 +803,11 @@ int vp8b200_seam_show(VP8D_COMP *pbi, YV12_BUFFER_CONFIG *sd)
     *sd = *cm->frame_to_show;
     if (!s || !s->ctx) return 0;               /* record-capture mode: no pixels */
     if (s->device_failed) return -1;
+    if (s->fetch_queued) {                       /* the engine copies it behind the frame's batch */
+        s->fetch_queued = 0;
+        s->fetch_pending = 1;
+        return 0;
+    }
     return seam_queue_fetch(pbi, s, cm->frame_to_show->buffer_alloc);
 }
 
@@ -806,16 +853,15 @@ int vp8b200_seam_get_raw_frame(VP8D_COMP *pbi, YV12_BUFFER_CONFIG *sd, int64_t *
         if (cm->show_frame && cm->frame_to_show) {
             const YV12_BUFFER_CONFIG *f = cm->frame_to_show;
             uint8_t *out;
-            if (!s->out_buf[0] || s->out_size != (size_t)f->frame_size) {
-                vp8b200_host_free(s->out_buf[0]); vp8b200_host_free(s->out_buf[1]);
-                s->out_buf[0] = (uint8_t *)vp8b200_host_alloc_on(seam_device(), (size_t)f->frame_size);
-                s->out_buf[1] = (uint8_t *)vp8b200_host_alloc_on(seam_device(), (size_t)f->frame_size);
-                s->out_size = (size_t)f->frame_size;
-                if (!s->out_buf[0] || !s->out_buf[1]) return seam_device_error(pbi, s, "pinned output image", VP8B200_ERR_NOMEM);
+            if (s->fetch_queued) {                /* the engine copies it behind the frame's batch */
+                out = s->fetch_queued_dst;
+                s->fetch_queued = 0;
+                s->fetch_pending = 1;
+            } else {
+                out = seam_out_buffer(s, (size_t)f->frame_size);
+                if (!out) return seam_device_error(pbi, s, "pinned output image", VP8B200_ERR_NOMEM);
+                if (seam_queue_fetch(pbi, s, out)) return -1;
             }
-            out = s->out_buf[s->out_cur];
-            s->out_cur ^= 1;
-            if (seam_queue_fetch(pbi, s, out)) return -1;
             s->delayed_sd = *f;
             s->delayed_sd.buffer_alloc = out;
             s->delayed_sd.y_buffer = out + (f->y_buffer - f->buffer_alloc);

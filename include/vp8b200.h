@@ -166,6 +166,19 @@ int vp8b200_frame_begin(vp8b200_ctx *ctx, const vp8b200_frame_hdr *hdr, vp8b200_
 /* Queue H2D of the records + every reconstruction kernel of the frame on the context's
  * stream and return without waiting.  n_aux / n_coef = entries actually written. */
 int vp8b200_frame_submit(vp8b200_ctx *ctx, uint32_t n_aux, uint32_t n_coef);
+/* Coalesced submit (SURVEY 8b "shared batch scheduler across ctxs", 8f N2): hand the frame to the
+ * per-device engine and return.  One engine thread per device gathers the frames that the
+ * decoder threads of all contexts have queued (bounded wait: VP8B200_BATCH_WINDOW_US, default
+ * 3000, until about half of the live contexts have a frame; a lone context is issued at once;
+ * VP8B200_BATCH_MAX frames at most) and issues ONE launch of each kernel over all of them, their
+ * record uploads before and - for show_fb >= 0 - the device->host copy of that frame buffer
+ * after (display_w/h as in vp8b200_frame_fetch_begin).  The caller's thread makes no CUDA
+ * launch; vp8b200_frame_fetch_wait is where it waits.  Errors of the issue are reported by the
+ * next call on the context. */
+int vp8b200_frame_submit_show(vp8b200_ctx *ctx, uint32_t n_aux, uint32_t n_coef,
+                              int show_fb, uint8_t *dst, int display_w, int display_h);
+/* [0] batches, [1] frames the engine of `device` has issued */
+void vp8b200_engine_stats(int device, uint64_t out[2]);
 /* Abandon a frame opened by frame_begin (the reference's longjmp error path). */
 int vp8b200_frame_abort(vp8b200_ctx *ctx);
 /* Wait for frame buffer `fb` and copy the whole allocation (borders included) to `dst`. */

@@ -13,8 +13,12 @@
 #include <string.h>
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 #include "vp8b200_internal.h"
 
@@ -87,6 +91,10 @@ struct vp8b200_ctx {
     bool batch_pending;            /* own stream has not yet waited for batch_ev */
     vp8b200_ctx *batch_leader;     /* whose stream that batch ran on */
     cudaEvent_t lead_ev[NBJOB];    /* as a leader: one event per in-flight batch */
+    /* per-device submit coalescer (see Engine below): frames handed to it / issued by it */
+    struct Engine *eng;
+    uint64_t eng_submitted, eng_issued;   /* eng_issued is written by the engine thread under its mutex */
+    int eng_status;                /* first error of an issue, reported by the next call on this context */
     char err[256];
 };
 
@@ -100,6 +108,47 @@ static const char *k_noerr = "";
             return VP8B200_ERR_CUDA;                                                       \
         }                                                                                  \
     } while (0)
+
+/* ---- per-device submit coalescer ("engine"), SURVEY 8b "shared batch scheduler across ctxs" ----
+ * vp8b200_frame_submit_show hands a parsed frame to the engine of the context's device and
+ * returns; ONE engine thread per device gathers what the decoder threads of all contexts have
+ * queued and issues it as one batch: the records' H2D copies, ONE launch of each kernel over
+ * all gathered frames (the same batched launch bench.py's resident replay uses), and the D2H
+ * copies of the frames that are shown.  Decoder threads make no CUDA launch at all; the only
+ * place they wait is vp8b200_frame_fetch_wait (vpx_codec_get_frame). */
+struct EngineSubmit {
+    vp8b200_ctx *c;
+    int slot;
+    uint32_t n_aux, n_coef;
+    unsigned n_intra, n_split;
+    vp8b200_frame_hdr hdr;
+    uint64_t seq;
+    int show_fb;                   /* < 0: not shown */
+    uint8_t *show_dst;
+    int show_w, show_h;
+};
+#define ENG_RING 8
+struct Engine {
+    int device;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::deque<EngineSubmit> q;
+    int n_ctx;                     /* contexts that have used this engine and are alive */
+    bool started, failed;
+    cudaStream_t stream[2], copy_stream;
+    FrameJob *h_jobs[ENG_RING], *d_jobs[ENG_RING];
+    cudaEvent_t jobs_ev[ENG_RING], batch_ev[ENG_RING];
+    bool ring_pending[ENG_RING];
+    int cap, cur;
+    unsigned *d_tickets[2];
+    unsigned ticket_base[2][2];
+    int window_us, max_batch;
+    std::atomic<uint64_t> batches{0}, frames{0};
+};
+static std::mutex g_eng_mu;
+static Engine *g_engines[64];
+static void engine_thread(Engine *e);
+static void engine_settle(vp8b200_ctx *c);
 
 extern "C" int vp8b200_abi_version(void) { return VP8B200_ABI_VERSION; }
 
@@ -148,10 +197,17 @@ static std::vector<vp8b200_ctx *> g_live;
 static void free_ctx(vp8b200_ctx *c)
 {
     if (!c) return;
+    engine_settle(c);
+    if (c->eng) {
+        std::lock_guard<std::mutex> lk(c->eng->mu);
+        c->eng->n_ctx--;
+        c->eng = NULL;
+    }
     cudaSetDevice(c->device);
     if (c->batch_pending) cudaEventSynchronize(c->batch_ev);   /* a batch on another leader's stream may still use us */
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->fetch_done) cudaEventSynchronize(c->fetch_done);    /* a copy queued by the engine on its own copy stream */
     {
         /* every batch this context led has finished now: members need not (and, once the
          * events below are destroyed, must not) wait for them any more */
@@ -361,6 +417,7 @@ extern "C" int vp8b200_frame_begin(vp8b200_ctx *c, const vp8b200_frame_hdr *hdr,
     if (!c || !hdr || !bufs || !hdr_ok(c, hdr)) return VP8B200_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     c->open = false;
+    if (c->eng_submitted - __atomic_load_n(&c->eng_issued, __ATOMIC_ACQUIRE) > (uint64_t)(NSLOT - 2)) engine_settle(c);
     Slot &s = c->slot[c->cur];
     if (s.pending) {                         /* the upload that last used this slot */
         CK(c, cudaEventSynchronize(s.h2d_done));
@@ -476,32 +533,37 @@ static void prof_mark(vp8b200_ctx *c, int kind, bool begin)
     }
 }
 
-static int run_jobs(vp8b200_ctx *c, const FrameJob *d_jobs, int n, bool any_inter, bool any_split,
-                    unsigned max_intra, bool any_lf)
+/* `st` / `tickets` / `ticket_base`: the launching stream and its two wavefront ticket counters
+ * (the context's own for frame_submit and batch_run, the engine's for coalesced submits) */
+static int run_jobs_on(vp8b200_ctx *c, cudaStream_t st, unsigned *tickets, unsigned *ticket_base,
+                       const FrameJob *d_jobs, int n, bool any_inter, bool any_split,
+                       unsigned max_intra, bool any_lf, bool prof)
 {
     const bool any_intra = max_intra > 0;
     int nctas = 0;
     unsigned k = 0;
     if (any_inter) {
-        prof_mark(c, 0, true);
-        vp8b200_launch_inter(c->stream, d_jobs, n, c->geo, any_split);
-        prof_mark(c, 0, false); k += any_split ? 2 : 1;
+        if (prof) prof_mark(c, 0, true);
+        vp8b200_launch_inter(st, d_jobs, n, c->geo, any_split);
+        if (prof) prof_mark(c, 0, false);
+        k += any_split ? 2 : 1;
     }
     if (any_intra) {
-        prof_mark(c, 1, true);
-        vp8b200_launch_intra(c->stream, d_jobs, n, c->geo, max_intra, c->d_tickets + 0, c->ticket_base[0], &nctas);
-        prof_mark(c, 1, false);
-        c->ticket_base[0] += (unsigned)nctas; k++;
+        if (prof) prof_mark(c, 1, true);
+        vp8b200_launch_intra(st, d_jobs, n, c->geo, max_intra, tickets + 0, ticket_base[0], &nctas);
+        if (prof) prof_mark(c, 1, false);
+        ticket_base[0] += (unsigned)nctas; k++;
     }
     if (any_lf) {
-        prof_mark(c, 2, true);
-        vp8b200_launch_loopfilter(c->stream, d_jobs, n, c->geo, c->d_tickets + 1, c->ticket_base[1], &nctas);
-        prof_mark(c, 2, false);
-        c->ticket_base[1] += (unsigned)nctas; k++;
+        if (prof) prof_mark(c, 2, true);
+        vp8b200_launch_loopfilter(st, d_jobs, n, c->geo, tickets + 1, ticket_base[1], &nctas);
+        if (prof) prof_mark(c, 2, false);
+        ticket_base[1] += (unsigned)nctas; k++;
     }
-    prof_mark(c, 3, true);
-    vp8b200_launch_border(c->stream, d_jobs, n, c->geo);
-    prof_mark(c, 3, false); k++;
+    if (prof) prof_mark(c, 3, true);
+    vp8b200_launch_border(st, d_jobs, n, c->geo);
+    if (prof) prof_mark(c, 3, false);
+    k++;
     c->launches += k;
     g_launches += k;
     g_frames += (uint64_t)n;
@@ -509,9 +571,16 @@ static int run_jobs(vp8b200_ctx *c, const FrameJob *d_jobs, int n, bool any_inte
     return VP8B200_OK;
 }
 
+static int run_jobs(vp8b200_ctx *c, const FrameJob *d_jobs, int n, bool any_inter, bool any_split,
+                    unsigned max_intra, bool any_lf)
+{
+    return run_jobs_on(c, c->stream, c->d_tickets, c->ticket_base, d_jobs, n, any_inter, any_split, max_intra, any_lf, true);
+}
+
 extern "C" int vp8b200_frame_submit(vp8b200_ctx *c, uint32_t n_aux, uint32_t n_coef)
 {
     if (!c || !c->open) return VP8B200_ERR_INVALID;
+    engine_settle(c);
     c->open = false;
     if (n_aux > c->n_mb || n_coef > c->n_mb * 25) return VP8B200_ERR_OVERFLOW;
     CK(c, cudaSetDevice(c->device));
@@ -549,11 +618,264 @@ extern "C" int vp8b200_frame_submit(vp8b200_ctx *c, uint32_t n_aux, uint32_t n_c
  * ((w+1)/2) x ((h+1)/2) chroma samples (vpxdec.c:1093-1115) - as three pitched copies that land
  * at the same offsets as in the device buffer, so img->planes[] / stride[] of the host mirror
  * stay valid (vp8_dx_iface.c:319-348). */
+
+/* ---- engine: queue, gather, issue ---------------------------------------------------------- */
+
+static Engine *engine_get(vp8b200_ctx *c)
+{
+    std::lock_guard<std::mutex> lk(g_eng_mu);
+    if (c->device < 0 || c->device >= 64) return NULL;
+    Engine *e = g_engines[c->device];
+    if (!e) {
+        e = new (std::nothrow) Engine();
+        if (!e) return NULL;
+        e->device = c->device;
+        e->n_ctx = 0; e->started = false; e->failed = false; e->cap = 0; e->cur = 0;
+        for (int i = 0; i < ENG_RING; i++) { e->h_jobs[i] = NULL; e->d_jobs[i] = NULL; e->ring_pending[i] = false; }
+        const char *w = getenv("VP8B200_BATCH_WINDOW_US");
+        e->window_us = w ? atoi(w) : 3000;
+        const char *m = getenv("VP8B200_BATCH_MAX");
+        e->max_batch = m ? atoi(m) : 64;
+        if (e->max_batch < 1) e->max_batch = 1;
+        g_engines[c->device] = e;
+    }
+    return e;
+}
+
+/* wait until the engine thread has issued everything this context handed over */
+static void engine_settle(vp8b200_ctx *c)
+{
+    /* acquire: everything the engine thread wrote into the context while issuing is visible */
+    if (!c || !c->eng || c->eng_submitted == __atomic_load_n(&c->eng_issued, __ATOMIC_ACQUIRE)) return;
+    Engine *e = c->eng;
+    std::unique_lock<std::mutex> lk(e->mu);
+    e->cv_done.wait(lk, [&] { return __atomic_load_n(&c->eng_issued, __ATOMIC_ACQUIRE) >= c->eng_submitted; });
+}
+
+#define ECK(call)                                                                          \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            snprintf(err, sizeof err, "%s: %s", #call, cudaGetErrorString(e_));           \
+            return VP8B200_ERR_CUDA;                                                       \
+        }                                                                                  \
+    } while (0)
+
+static int engine_init_device(Engine *e, char (&err)[256])
+{
+    ECK(cudaSetDevice(e->device));
+    for (int i = 0; i < 2; i++) {
+        ECK(cudaStreamCreateWithFlags(&e->stream[i], cudaStreamNonBlocking));
+        ECK(cudaMalloc((void **)&e->d_tickets[i], 2 * sizeof(unsigned)));
+        ECK(cudaMemset(e->d_tickets[i], 0, 2 * sizeof(unsigned)));
+        e->ticket_base[i][0] = e->ticket_base[i][1] = 0;
+    }
+    ECK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < ENG_RING; i++) {
+        ECK(cudaEventCreateWithFlags(&e->jobs_ev[i], cudaEventDisableTiming));
+        ECK(cudaEventCreateWithFlags(&e->batch_ev[i], cudaEventDisableTiming));
+    }
+    return VP8B200_OK;
+}
+
+/* one batch: frames of DISTINCT contexts with the same geometry */
+static int engine_issue(Engine *e, std::vector<EngineSubmit> &b, char (&err)[256])
+{
+    const int n = (int)b.size();
+    vp8b200_ctx *c0 = b[0].c;
+    if (n > e->cap) {
+        ECK(cudaDeviceSynchronize());
+        for (int i = 0; i < ENG_RING; i++) {
+            cudaFreeHost(e->h_jobs[i]); cudaFree(e->d_jobs[i]);
+            e->h_jobs[i] = NULL; e->d_jobs[i] = NULL; e->ring_pending[i] = false;
+            ECK(cudaHostAlloc((void **)&e->h_jobs[i], (size_t)n * sizeof(FrameJob), cudaHostAllocPortable));
+            ECK(cudaMalloc((void **)&e->d_jobs[i], (size_t)n * sizeof(FrameJob)));
+        }
+        e->cap = n;
+    }
+    const int r = e->cur;
+    e->cur = (r + 1) % ENG_RING;
+    const int si = r & 1;                                  /* consecutive batches alternate streams: */
+    cudaStream_t st = e->stream[si];                       /* the copies of one overlap the kernels of the other */
+    if (e->ring_pending[r]) { ECK(cudaEventSynchronize(e->jobs_ev[r])); e->ring_pending[r] = false; }
+    bool any_inter = false, any_lf = false, any_split = false;
+    unsigned max_intra = 0;
+    for (int i = 0; i < n; i++) {
+        EngineSubmit &sb = b[i];
+        vp8b200_ctx *c = sb.c;
+        Slot &s = c->slot[sb.slot];
+        const vp8b200_frame_hdr &h = sb.hdr;
+        const bool key = h.frame_type == 0;
+        /* order behind whatever last touched this context: a batch on the other engine stream or
+         * under a batch_run leader, work on its own stream, a copy still reading the new buffer */
+        if (c->batch_pending) { ECK(cudaStreamWaitEvent(st, c->batch_ev, 0)); c->batch_pending = false; }
+        if (c->own_dirty) {
+            ECK(cudaEventRecord(c->own_ev, c->stream));
+            ECK(cudaStreamWaitEvent(st, c->own_ev, 0));
+            c->own_dirty = false;
+        }
+        if (c->fetch_fb >= 0 && c->fetch_fb == h.fb_new) { ECK(cudaStreamWaitEvent(st, c->fetch_done, 0)); c->fetch_fb = -1; }
+        if (!key && sb.n_intra)
+            ECK(cudaMemcpyAsync(s.d_ilist, s.h_ilist, (size_t)sb.n_intra * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        ECK(cudaMemcpyAsync(s.d_mb, s.h_mb, (size_t)c->n_mb * sizeof(vp8b200_mb), cudaMemcpyHostToDevice, st));
+        if (sb.n_aux) ECK(cudaMemcpyAsync(s.d_aux, s.h_aux, (size_t)sb.n_aux * sizeof(vp8b200_aux), cudaMemcpyHostToDevice, st));
+        if (sb.n_coef) ECK(cudaMemcpyAsync(s.d_coef, s.h_coef, (size_t)sb.n_coef * 32, cudaMemcpyHostToDevice, st));
+        ECK(cudaEventRecord(s.h2d_done, st));
+        s.pending = true;
+        g_h2d_bytes += (uint64_t)c->n_mb * sizeof(vp8b200_mb) + (uint64_t)sb.n_aux * sizeof(vp8b200_aux) +
+                       (uint64_t)sb.n_coef * 32 + sizeof(FrameJob) + (key ? 0 : (uint64_t)sb.n_intra * 4);
+        any_inter |= !key; any_lf |= h.filter_level != 0; any_split |= sb.n_split > 0;
+        if (sb.n_intra > max_intra) max_intra = sb.n_intra;
+    }
+    for (int i = 0; i < n; i++) {
+        EngineSubmit &sb = b[i];
+        Slot &s = sb.c->slot[sb.slot];
+        fill_job(sb.c, &e->h_jobs[r][i], sb.hdr, s.d_mb, s.d_aux, s.d_coef, sb.hdr.frame_type == 0 ? NULL : s.d_ilist,
+                 sb.n_intra, sb.n_split, sb.n_intra > 0, any_lf && sb.hdr.filter_level != 0);
+    }
+    ECK(cudaMemcpyAsync(e->d_jobs[r], e->h_jobs[r], (size_t)n * sizeof(FrameJob), cudaMemcpyHostToDevice, st));
+    ECK(cudaEventRecord(e->jobs_ev[r], st));
+    e->ring_pending[r] = true;
+    {
+        /* launch bookkeeping goes to the first member (vp8b200_launch_count is per context) */
+        int rs = run_jobs_on(c0, st, e->d_tickets[si], e->ticket_base[si], e->d_jobs[r], n, any_inter, any_split, max_intra, any_lf, false);
+        if (rs) { snprintf(err, sizeof err, "%s", c0->err); return rs; }
+    }
+    ECK(cudaEventRecord(e->batch_ev[r], st));
+    bool any_show = false;
+    for (int i = 0; i < n; i++) {
+        vp8b200_ctx *c = b[i].c;
+        c->batch_ev = e->batch_ev[r]; c->batch_pending = true; c->batch_leader = NULL;
+        any_show |= b[i].show_fb >= 0;
+    }
+    if (any_show) {
+        ECK(cudaStreamWaitEvent(e->copy_stream, e->batch_ev[r], 0));
+        for (int i = 0; i < n; i++) {
+            EngineSubmit &sb = b[i];
+            if (sb.show_fb < 0) continue;
+            vp8b200_ctx *c = sb.c;
+            const Geo &g = c->geo;
+            if (sb.show_w == 0) {
+                ECK(cudaMemcpyAsync(sb.show_dst, c->fb[sb.show_fb], c->frame_size, cudaMemcpyDeviceToHost, e->copy_stream));
+                g_d2h_bytes += c->frame_size;
+            } else {
+                const int cw = (sb.show_w + 1) >> 1, ch = (sb.show_h + 1) >> 1;
+                ECK(cudaMemcpy2DAsync(sb.show_dst + g.y_off, (size_t)g.y_stride, c->fb[sb.show_fb] + g.y_off, (size_t)g.y_stride,
+                                      (size_t)sb.show_w, (size_t)sb.show_h, cudaMemcpyDeviceToHost, e->copy_stream));
+                ECK(cudaMemcpy2DAsync(sb.show_dst + g.u_off, (size_t)g.uv_stride, c->fb[sb.show_fb] + g.u_off, (size_t)g.uv_stride,
+                                      (size_t)cw, (size_t)ch, cudaMemcpyDeviceToHost, e->copy_stream));
+                ECK(cudaMemcpy2DAsync(sb.show_dst + g.v_off, (size_t)g.uv_stride, c->fb[sb.show_fb] + g.v_off, (size_t)g.uv_stride,
+                                      (size_t)cw, (size_t)ch, cudaMemcpyDeviceToHost, e->copy_stream));
+                g_d2h_bytes += (uint64_t)sb.show_w * sb.show_h + 2ull * cw * ch;
+            }
+            ECK(cudaEventRecord(c->fetch_done, e->copy_stream));
+            c->fetch_fb = sb.show_fb;
+        }
+    }
+    e->batches++;
+    e->frames += (uint64_t)n;
+    return VP8B200_OK;
+}
+
+static void engine_thread(Engine *e)
+{
+    char err[256] = "";
+    int init = engine_init_device(e, err);
+    std::vector<EngineSubmit> batch, rest;
+    for (;;) {
+        batch.clear();
+        {
+            std::unique_lock<std::mutex> lk(e->mu);
+            e->cv_work.wait(lk, [&] { return !e->q.empty(); });
+            /* gather: with several contexts alive wait (bounded) until about half of them have a
+             * frame queued; a lone context is issued at once */
+            const int target = std::min(e->max_batch, std::max(1, e->n_ctx / 2));
+            if ((int)e->q.size() < target && e->window_us > 0) {
+                const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(e->window_us);
+                e->cv_work.wait_until(lk, deadline, [&] { return (int)e->q.size() >= target; });
+            }
+            /* at most one frame per context (a later frame depends on the earlier one), one geometry */
+            rest.clear();
+            const vp8b200_ctx *g0 = e->q.front().c;
+            while (!e->q.empty()) {
+                EngineSubmit sb = e->q.front();
+                e->q.pop_front();
+                bool take = (int)batch.size() < e->max_batch && sb.c->geo.width == g0->geo.width && sb.c->geo.height == g0->geo.height;
+                for (size_t k = 0; take && k < batch.size(); k++) if (batch[k].c == sb.c) take = false;
+                for (size_t k = 0; take && k < rest.size(); k++) if (rest[k].c == sb.c) take = false;   /* keep per-context order */
+                (take ? batch : rest).push_back(sb);
+            }
+            for (auto &sb : rest) e->q.push_back(sb);
+        }
+        int st = init ? init : (e->failed ? VP8B200_ERR_CUDA : engine_issue(e, batch, err));
+        if (st && !init) e->failed = true;                 /* a CUDA failure is sticky for the device */
+        {
+            std::lock_guard<std::mutex> lk(e->mu);
+            for (auto &sb : batch) {
+                if (st) { sb.c->eng_status = st; snprintf(sb.c->err, sizeof sb.c->err, "engine: %s", err); }
+                __atomic_store_n(&sb.c->eng_issued, sb.seq, __ATOMIC_RELEASE);
+            }
+        }
+        e->cv_done.notify_all();
+    }
+}
+
+/* Coalesced submit: validate on the caller's thread, hand the frame to the
+ * device's engine, return.  show_fb >= 0 also queues the device->host copy of that buffer (as
+ * vp8b200_frame_fetch_begin would: display_w/h = 0 -> whole allocation) behind the frame's
+ * kernels; vp8b200_frame_fetch_wait is then the caller's only wait. */
+extern "C" int vp8b200_frame_submit_show(vp8b200_ctx *c, uint32_t n_aux, uint32_t n_coef,
+                                         int show_fb, uint8_t *dst, int display_w, int display_h)
+{
+    if (!c || !c->open) return VP8B200_ERR_INVALID;
+    c->open = false;
+    if (n_aux > c->n_mb || n_coef > c->n_mb * 25) return VP8B200_ERR_OVERFLOW;
+    if (show_fb >= c->n_fb || (show_fb >= 0 && (!dst || display_w < 0 || display_h < 0 || display_w > c->geo.width ||
+                                                 display_h > c->geo.height || (display_w == 0) != (display_h == 0))))
+        return VP8B200_ERR_INVALID;
+    if (c->eng_status) { int st = c->eng_status; c->eng_status = 0; return st; }
+    if (!c->eng) {
+        Engine *e = engine_get(c);
+        if (!e) return VP8B200_ERR_NOMEM;
+        std::lock_guard<std::mutex> lk(e->mu);
+        if (!e->started) { e->started = true; std::thread(engine_thread, e).detach(); }
+        e->n_ctx++;
+        c->eng = e;
+    }
+    Slot &s = c->slot[c->cur];
+    EngineSubmit sb;
+    sb.c = c; sb.slot = c->cur; sb.n_aux = n_aux; sb.n_coef = n_coef; sb.hdr = c->cur_hdr;
+    sb.show_fb = show_fb; sb.show_dst = dst; sb.show_w = display_w; sb.show_h = display_h;
+    if (!scan_records(c->geo, s.h_mb, s.h_aux, n_aux, n_coef, sb.hdr.frame_type == 0, s.h_ilist, c->diag_tmp, &sb.n_intra, &sb.n_split)) {
+        snprintf(c->err, sizeof c->err, "macroblock records failed validation");
+        return VP8B200_ERR_INVALID;
+    }
+    c->cur = (c->cur + 1) % NSLOT;
+    {
+        std::lock_guard<std::mutex> lk(c->eng->mu);
+        sb.seq = ++c->eng_submitted;
+        c->eng->q.push_back(sb);
+    }
+    c->eng->cv_work.notify_one();
+    return VP8B200_OK;
+}
+
+/* engine statistics of the context's device: [0] batches issued, [1] frames issued */
+extern "C" void vp8b200_engine_stats(int device, uint64_t out[2])
+{
+    out[0] = out[1] = 0;
+    std::lock_guard<std::mutex> lk(g_eng_mu);
+    if (device >= 0 && device < 64 && g_engines[device]) {
+        out[0] = g_engines[device]->batches.load(); out[1] = g_engines[device]->frames.load();
+    }
+}
+
 extern "C" int vp8b200_frame_fetch_begin(vp8b200_ctx *c, int fb, uint8_t *dst, int display_w, int display_h)
 {
     if (!c || fb < 0 || fb >= c->n_fb || !dst || display_w < 0 || display_h < 0 ||
         display_w > c->geo.width || display_h > c->geo.height || (display_w == 0) != (display_h == 0))
         return VP8B200_ERR_INVALID;
+    engine_settle(c);
     CK(c, cudaSetDevice(c->device));
     { int js = join_batch(c); if (js) return js; }
     if (c->fetch_fb >= 0) {
@@ -588,6 +910,8 @@ extern "C" int vp8b200_frame_fetch_begin(vp8b200_ctx *c, int fb, uint8_t *dst, i
 extern "C" int vp8b200_frame_fetch_wait(vp8b200_ctx *c)
 {
     if (!c) return VP8B200_ERR_INVALID;
+    engine_settle(c);                               /* the copy is queued by the engine thread */
+    if (c->eng_status) { int st = c->eng_status; c->eng_status = 0; return st; }
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaEventSynchronize(c->fetch_done));
     c->fetch_fb = -1;
@@ -597,6 +921,7 @@ extern "C" int vp8b200_frame_fetch_wait(vp8b200_ctx *c)
 extern "C" int vp8b200_frame_fetch(vp8b200_ctx *c, int fb, uint8_t *dst, size_t bytes)
 {
     if (!c || fb < 0 || fb >= c->n_fb || !dst || bytes > c->frame_size) return VP8B200_ERR_INVALID;
+    engine_settle(c);
     if (bytes == c->frame_size) {
         int st = vp8b200_frame_fetch_begin(c, fb, dst, 0, 0);
         return st ? st : vp8b200_frame_fetch_wait(c);
@@ -612,6 +937,7 @@ extern "C" int vp8b200_frame_fetch(vp8b200_ctx *c, int fb, uint8_t *dst, size_t 
 extern "C" int vp8b200_frame_upload(vp8b200_ctx *c, int fb, const uint8_t *src, size_t bytes)
 {
     if (!c || fb < 0 || fb >= c->n_fb || !src || bytes > c->frame_size) return VP8B200_ERR_INVALID;
+    engine_settle(c);
     CK(c, cudaSetDevice(c->device));
     { int js = join_batch(c); if (js) return js; }
     { int os = order_after_fetch(c, c->stream, fb); if (os) return os; }
@@ -625,6 +951,7 @@ extern "C" int vp8b200_frame_copy(vp8b200_ctx *c, int fb_dst, int fb_src)
 {
     if (!c || fb_dst < 0 || fb_dst >= c->n_fb || fb_src < 0 || fb_src >= c->n_fb) return VP8B200_ERR_INVALID;
     if (fb_dst == fb_src) return VP8B200_OK;
+    engine_settle(c);
     CK(c, cudaSetDevice(c->device));
     { int js = join_batch(c); if (js) return js; }
     { int os = order_after_fetch(c, c->stream, fb_dst); if (os) return os; }
@@ -636,6 +963,7 @@ extern "C" int vp8b200_frame_copy(vp8b200_ctx *c, int fb_dst, int fb_src)
 extern "C" int vp8b200_sync(vp8b200_ctx *c)
 {
     if (!c) return VP8B200_ERR_INVALID;
+    engine_settle(c);
     CK(c, cudaSetDevice(c->device));
     { int js = join_batch(c); if (js) return js; }
     CK(c, cudaStreamSynchronize(c->stream));
@@ -722,6 +1050,7 @@ extern "C" int vp8b200_batch_run(vp8b200_ctx *const *ctx, vp8b200_staged *const 
             return VP8B200_ERR_INVALID;
         for (int k = 0; k < i; k++) if (ctx[k] == ctx[i]) return VP8B200_ERR_INVALID;
     }
+    for (int i = 0; i < n; i++) engine_settle(ctx[i]);
     CK(c, cudaSetDevice(c->device));
     if (n > c->bjobs_cap) {
         CK(c, cudaStreamSynchronize(c->stream));

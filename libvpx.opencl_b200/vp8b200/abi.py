@@ -17,7 +17,7 @@ EXPORTS = [
     "vp8b200_create", "vp8b200_destroy", "vp8b200_frame_size", "vp8b200_y_stride",
     "vp8b200_host_alloc", "vp8b200_host_alloc_on", "vp8b200_host_free", "vp8b200_frame_fetch_begin",
     "vp8b200_frame_fetch_wait", "vp8b200_frame_begin", "vp8b200_frame_submit",
-    "vp8b200_frame_abort", "vp8b200_frame_fetch", "vp8b200_frame_upload", "vp8b200_frame_copy",
+    "vp8b200_frame_abort", "vp8b200_frame_submit_show", "vp8b200_engine_stats", "vp8b200_frame_fetch", "vp8b200_frame_upload", "vp8b200_frame_copy",
     "vp8b200_sync", "vp8b200_stage_frame", "vp8b200_staged_free", "vp8b200_batch_run",
     "vp8b200_launch_count", "vp8b200_stream", "vp8b200_global_stats", "vp8b200_profile_enable",
     "vp8b200_profile_read",
@@ -52,6 +52,9 @@ def lib():
         L.vp8b200_frame_begin.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(FrameBufs)]
         L.vp8b200_frame_submit.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
         L.vp8b200_frame_abort.argtypes = [C.c_void_p]
+        L.vp8b200_frame_submit_show.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        L.vp8b200_engine_stats.restype = None
+        L.vp8b200_engine_stats.argtypes = [C.c_int, C.POINTER(C.c_uint64)]
         L.vp8b200_frame_fetch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
         L.vp8b200_frame_fetch_begin.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
         L.vp8b200_frame_fetch_wait.argtypes = [C.c_void_p]
@@ -128,6 +131,23 @@ class Context:
         if fr.n_coef:
             C.memmove(bufs.coef, fr.coef.ctypes.data, 32 * fr.n_coef)
         self._ck(self.L.vp8b200_frame_submit(self.h, fr.n_aux, fr.n_coef), "frame_submit")
+
+    def submit_show(self, fr, show_fb=-1, out=None, display=(0, 0)):
+        """frame_begin + fill + frame_submit_show: the coalesced path (engine thread issues)."""
+        hdr = np.asarray(fr.hdr, HDR_DTYPE).tobytes()
+        bufs = FrameBufs()
+        self._ck(self.L.vp8b200_frame_begin(self.h, hdr, C.byref(bufs)), "frame_begin")
+        C.memmove(bufs.mb, fr.mb.ctypes.data, 16 * self.n_mb)
+        if fr.n_aux:
+            C.memmove(bufs.aux, fr.aux.ctypes.data, 64 * fr.n_aux)
+        if fr.n_coef:
+            C.memmove(bufs.coef, fr.coef.ctypes.data, 32 * fr.n_coef)
+        dst = out.ctypes.data_as(C.c_void_p) if out is not None else None
+        self._ck(self.L.vp8b200_frame_submit_show(self.h, fr.n_aux, fr.n_coef, show_fb, dst, display[0], display[1]),
+                 "frame_submit_show")
+
+    def fetch_wait(self):
+        self._ck(self.L.vp8b200_frame_fetch_wait(self.h), "frame_fetch_wait")
 
     def fetch(self, fb, out=None):
         if out is None:

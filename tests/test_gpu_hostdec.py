@@ -67,6 +67,12 @@ def test_lazy_fetch_pipeline_and_frame_delay_deliver_the_same_pixels(gpu_lib):
     for r in (pipe, delay, one):
         assert r["frames"] == base["frames"] and r["checksum"] == base["checksum"]
     assert delay["frame_delay"] == 1 and pipe["pipeline"] == 1
+    assert base["engine_frames"] >= base["frames"] and base["engine_batches"] <= base["engine_frames"]
+    direct = _bench("--threads", "2", "--streams", "4", "--repeat", "2", "--touch", env=dict(os.environ, VP8B200_COALESCE="0"))
+    assert direct["checksum"] == base["checksum"] and direct["engine_frames"] == 0
+    many = _bench("--threads", "4", "--streams", "12", "--repeat", "2", "--touch", "--pipeline")
+    assert many["checksum"] == 3 * base["checksum"]
+    assert many["engine_batches"] < many["engine_frames"], "the engine never put two streams into one launch"
     full = _bench("--threads", "2", "--streams", "4", "--repeat", "2", "--touch", env=dict(os.environ, VP8B200_FETCH="full"))
     assert full["checksum"] == base["checksum"] and full["d2h_bytes"] > base["d2h_bytes"]
     # visible samples only: 1.5 * W * H bytes per shown frame (N3)

@@ -226,3 +226,50 @@ def test_leader_destroyed_before_its_batch_members(gpu_lib):
         _compare(ctxs[s].fetch(2), oras[s].fb(2), geo, "member %d in the second batch" % s)
     for c in ctxs[1:]:
         c.close()
+
+
+def test_coalesced_submit_batches_frames_of_many_contexts(gpu_lib):
+    """SURVEY 8b "shared batch scheduler across ctxs": vp8b200_frame_submit_show hands frames to
+    the per-device engine, whose thread issues ONE launch of each kernel over the frames of all
+    contexts that queued one, plus their uploads and the copies of the shown pictures.  Results
+    must equal the oracle's, frame after frame (every frame predicts from the previous one), and
+    the engine must really have batched."""
+    import ctypes as C
+    n_streams, mb_cols, mb_rows, n_frames = 8, 11, 7, 5
+    w, h = mb_cols * 16, mb_rows * 16
+    geo = frames.Geometry(w, h)
+    rng = np.random.default_rng(77)
+    ctxs = [abi.Context(w, h, 4) for _ in range(n_streams)]
+    oras = [OracleDecoder(w, h, 4) for _ in range(n_streams)]
+    for c, o in zip(ctxs, oras):
+        for fb, buf in enumerate(randrec.random_buffers(rng, geo.frame_size, 4)):
+            c.upload(fb, buf)
+            o.fb(fb)[:] = buf
+    st0 = (C.c_uint64 * 2)()
+    gpu_lib.vp8b200_engine_stats(0, st0)
+    fbs = [0, 1, 2, 3]
+    outs = [np.zeros(geo.frame_size, np.uint8) for _ in range(n_streams)]
+    for f in range(n_frames):
+        frs = [randrec.random_frame(rng, mb_cols, mb_rows, key=(f == 0 and s % 2 == 0), p_intra=0.1, fbs=tuple(fbs))
+               for s in range(n_streams)]
+        for s in range(n_streams):                           # every decoder queues its frame ...
+            ctxs[s].submit_show(frs[s], show_fb=fbs[0], out=outs[s], display=(w - 5, h - 3))
+        for s in range(n_streams):                           # ... and only then waits for its picture
+            ctxs[s].fetch_wait()
+            oras[s].frame(frs[s])
+            want = oras[s].fb(fbs[0])
+            assert geo.i420(outs[s], w - 5, h - 3) == geo.i420(want, w - 5, h - 3), (f, s)
+        # the whole buffer (borders included) through the synchronous fetch of the same context
+        _compare(ctxs[3].fetch(fbs[0]), oras[3].fb(fbs[0]), geo, "coalesced frame %d stream 3" % f)
+        fbs = fbs[1:] + fbs[:1]
+    st1 = (C.c_uint64 * 2)()
+    gpu_lib.vp8b200_engine_stats(0, st1)
+    assert st1[1] - st0[1] == n_streams * n_frames
+    assert st1[0] - st0[0] < n_streams * n_frames, "no two frames ever shared a launch"
+    # mixing with the direct path on the same context keeps the order
+    fr = randrec.random_frame(rng, mb_cols, mb_rows, fbs=tuple(fbs))
+    ctxs[0].submit(fr)
+    oras[0].frame(fr)
+    _compare(ctxs[0].fetch(fbs[0]), oras[0].fb(fbs[0]), geo, "direct submit after coalesced ones")
+    for c in ctxs:
+        c.close()

@@ -32,7 +32,10 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 
 # name: (kind, size, frames, seed, vpxenc args)
 CASES = {
-    # C1 of BASELINE.json (first 30 frames' worth of the same settings)
+    # C1 of BASELINE.json / SURVEY.md 8d exactly: CIF, 60 frames, seed 1, moving gradient + noise
+    "c1_cif": ("gradient", "352x288", 60, 1,
+               ["--good", "--cpu-used=2", "--target-bitrate=800", "--kf-max-dist=30"]),
+    # a shorter CIF clip with a second key frame inside 30 frames (smoke test, bench harness tests)
     "cif_p0": ("gradient", "352x288", 30, 1,
                ["--good", "--cpu-used=2", "--target-bitrate=800", "--kf-max-dist=20"]),
     # profile 1: bilinear MC + simple loop filter

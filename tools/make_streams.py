@@ -28,15 +28,15 @@ C2 = ["--good", "--cpu-used=3", "--profile=0", "--kf-max-dist=9999", "--auto-alt
 def cases(n_c5):
     c = {
         # C2: 720p P-frame-heavy, profile 0 (six-tap, normal loop filter)
-        "c2_720p": ("texture", "1280x720", 60, 2, C2 + ["--target-bitrate=3000"]),
+        "c2_720p": ("texture", "1280x720", 120, 2, C2 + ["--target-bitrate=3000"]),
         # C3: 1080p profile 3 (bilinear, full pixel; the encoder forces filter_level 0)
-        "c3_1080p_p3": ("texture", "1920x1080", 30, 3, ["--good", "--cpu-used=3", "--profile=3",
+        "c3_1080p_p3": ("texture", "1920x1080", 60, 3, ["--good", "--cpu-used=3", "--profile=3",
                                                           "--target-bitrate=6000", "--kf-max-dist=9999"]),
         # C3b: profile 1 so that the SIMPLE loop filter really runs (SURVEY.md 8d caveat)
-        "c3b_1080p_p1": ("texture", "1920x1080", 30, 3, ["--good", "--cpu-used=3", "--profile=1",
+        "c3b_1080p_p1": ("texture", "1920x1080", 60, 3, ["--good", "--cpu-used=3", "--profile=1",
                                                            "--target-bitrate=6000", "--kf-max-dist=9999"]),
         # C4: 2160p high motion, 8 token partitions, error resilient (segmentation)
-        "c4_2160p": ("motion", "3840x2160", 12, 4, ["--rt", "--cpu-used=4", "--token-parts=3",
+        "c4_2160p": ("motion", "3840x2160", 30, 4, ["--rt", "--cpu-used=4", "--token-parts=3",
                                                      "--error-resilient=1", "--target-bitrate=20000"]),
     }
     # C5: independent 1080p streams, C2-style settings, seeds 100..
