@@ -169,7 +169,7 @@ int vp8b200_frame_submit(vp8b200_ctx *ctx, uint32_t n_aux, uint32_t n_coef);
 /* Coalesced submit (SURVEY 8b "shared batch scheduler across ctxs", 8f N2): hand the frame to the
  * per-device engine and return.  One engine thread per device gathers the frames that the
  * decoder threads of all contexts have queued (bounded wait: VP8B200_BATCH_WINDOW_US, default
- * 3000, until about half of the live contexts have a frame; a lone context is issued at once;
+ * 1000, until about half of the live contexts have a frame; a lone context is issued at once;
  * VP8B200_BATCH_MAX frames at most) and issues ONE launch of each kernel over all of them, their
  * record uploads before and - for show_fb >= 0 - the device->host copy of that frame buffer
  * after (display_w/h as in vp8b200_frame_fetch_begin).  The caller's thread makes no CUDA

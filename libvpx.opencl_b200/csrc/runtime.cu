@@ -13,6 +13,10 @@
 #include <string.h>
 #include <algorithm>
 #include <atomic>
+#include <linux/futex.h>
+#include <sys/resource.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 #include <chrono>
 #include <condition_variable>
 #include <deque>
@@ -93,7 +97,8 @@ struct vp8b200_ctx {
     cudaEvent_t lead_ev[NBJOB];    /* as a leader: one event per in-flight batch */
     /* per-device submit coalescer (see Engine below): frames handed to it / issued by it */
     struct Engine *eng;
-    uint64_t eng_submitted, eng_issued;   /* eng_issued is written by the engine thread under its mutex */
+    uint64_t eng_submitted;        /* frames handed to the engine (decoder thread) */
+    uint32_t eng_issued;           /* ... issued by it (engine thread; a futex word: the decoder thread sleeps on it) */
     int eng_status;                /* first error of an issue, reported by the next call on this context */
     char err[256];
 };
@@ -417,7 +422,7 @@ extern "C" int vp8b200_frame_begin(vp8b200_ctx *c, const vp8b200_frame_hdr *hdr,
     if (!c || !hdr || !bufs || !hdr_ok(c, hdr)) return VP8B200_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     c->open = false;
-    if (c->eng_submitted - __atomic_load_n(&c->eng_issued, __ATOMIC_ACQUIRE) > (uint64_t)(NSLOT - 2)) engine_settle(c);
+    if ((uint32_t)c->eng_submitted - __atomic_load_n(&c->eng_issued, __ATOMIC_ACQUIRE) > (uint32_t)(NSLOT - 2)) engine_settle(c);
     Slot &s = c->slot[c->cur];
     if (s.pending) {                         /* the upload that last used this slot */
         CK(c, cudaEventSynchronize(s.h2d_done));
@@ -633,7 +638,7 @@ static Engine *engine_get(vp8b200_ctx *c)
         e->n_ctx = 0; e->started = false; e->failed = false; e->cap = 0; e->cur = 0;
         for (int i = 0; i < ENG_RING; i++) { e->h_jobs[i] = NULL; e->d_jobs[i] = NULL; e->ring_pending[i] = false; }
         const char *w = getenv("VP8B200_BATCH_WINDOW_US");
-        e->window_us = w ? atoi(w) : 3000;
+        e->window_us = w ? atoi(w) : 1000;
         const char *m = getenv("VP8B200_BATCH_MAX");
         e->max_batch = m ? atoi(m) : 64;
         if (e->max_batch < 1) e->max_batch = 1;
@@ -645,11 +650,15 @@ static Engine *engine_get(vp8b200_ctx *c)
 /* wait until the engine thread has issued everything this context handed over */
 static void engine_settle(vp8b200_ctx *c)
 {
-    /* acquire: everything the engine thread wrote into the context while issuing is visible */
-    if (!c || !c->eng || c->eng_submitted == __atomic_load_n(&c->eng_issued, __ATOMIC_ACQUIRE)) return;
-    Engine *e = c->eng;
-    std::unique_lock<std::mutex> lk(e->mu);
-    e->cv_done.wait(lk, [&] { return __atomic_load_n(&c->eng_issued, __ATOMIC_ACQUIRE) >= c->eng_submitted; });
+    /* acquire: everything the engine thread wrote into the context while issuing is visible.
+     * The wait is a futex on the context's own word: a batch wakes exactly its members. */
+    if (!c || !c->eng) return;
+    const uint32_t want = (uint32_t)c->eng_submitted;
+    for (;;) {
+        const uint32_t have = __atomic_load_n(&c->eng_issued, __ATOMIC_ACQUIRE);
+        if (have == want) return;
+        syscall(SYS_futex, &c->eng_issued, FUTEX_WAIT_PRIVATE, have, NULL, NULL, 0);
+    }
 }
 
 #define ECK(call)                                                                          \
@@ -780,6 +789,10 @@ static int engine_issue(Engine *e, std::vector<EngineSubmit> &b, char (&err)[256
 static void engine_thread(Engine *e)
 {
     char err[256] = "";
+    /* the engine sleeps most of the time and must run the moment a frame is queued, also on a
+     * host whose cores are all busy parsing: ask for a better scheduling priority (needs
+     * CAP_SYS_NICE; silently stays at the default otherwise) */
+    setpriority(PRIO_PROCESS, (id_t)syscall(SYS_gettid), -10);
     int init = engine_init_device(e, err);
     std::vector<EngineSubmit> batch, rest;
     for (;;) {
@@ -813,10 +826,10 @@ static void engine_thread(Engine *e)
             std::lock_guard<std::mutex> lk(e->mu);
             for (auto &sb : batch) {
                 if (st) { sb.c->eng_status = st; snprintf(sb.c->err, sizeof sb.c->err, "engine: %s", err); }
-                __atomic_store_n(&sb.c->eng_issued, sb.seq, __ATOMIC_RELEASE);
+                __atomic_store_n(&sb.c->eng_issued, (uint32_t)sb.seq, __ATOMIC_RELEASE);
+                syscall(SYS_futex, &sb.c->eng_issued, FUTEX_WAKE_PRIVATE, 1, NULL, NULL, 0);
             }
         }
-        e->cv_done.notify_all();
     }
 }
 
