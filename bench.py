@@ -78,19 +78,62 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """SM clock / throttle reasons DURING the timed region: NVML polled every few ms from a
+    thread (the timed region is ~0.1 s, shorter than nvidia-smi's loop period), nvidia-smi -lms
+    as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, gpu):
-        self.gpu, self.rows, self.p = gpu, [], None
+    def __init__(self, gpu, bus_id=None):
+        self.gpu, self.bus_id, self.rows, self.p, self.nv = gpu, bus_id, [], None, None
+        self.sm, self.mx, self.reasons, self.source = [], [], set(), None
+        self.halt = threading.Event()
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        if self.bus_id:
+            try:
+                return pynvml, pynvml.nvmlDeviceGetHandleByPciBusId(self.bus_id.encode())
+            except pynvml.NVMLError:
+                pass
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = self.gpu
+        if vis and all(x.strip().isdigit() for x in vis.split(",")):
+            idx = int(vis.split(",")[self.gpu])
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+
+    def _poll(self):
+        nv, h = self.nv
+        bits = [(nv.nvmlClocksThrottleReasonHwSlowdown, 0), (nv.nvmlClocksThrottleReasonHwThermalSlowdown, 1),
+                (nv.nvmlClocksThrottleReasonSwThermalSlowdown, 2), (nv.nvmlClocksThrottleReasonSwPowerCap, 3)]
+        while True:                              # at least one sample even for a very short region
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.reasons.update(self.NAMES[i] for b, i in bits if r & b)
+            except nv.NVMLError:
+                break
+            if self.halt.wait(0.004):
+                break
 
     def start(self):
+        try:
+            self.nv = self._nvml_handle()
+            self.mx = [float(self.nv[0].nvmlDeviceGetMaxClockInfo(self.nv[1], self.nv[0].NVML_CLOCK_SM))]
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                        "--format=csv,noheader,nounits", "-lms", "100"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -101,16 +144,28 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
-        if not self.p:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
-        self.t.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": reasons}
+        if self.nv:
+            self.halt.set()
+            self.t.join(timeout=2)
+        elif self.p:
+            self.p.terminate()
+            self.t.join(timeout=2)
+            self.sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+            self.mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+            self.reasons = {self.NAMES[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"}
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None,
+                "sm_max_mhz": max(self.mx) if self.mx else None,
+                "samples": len(self.sm), "source": self.source, "reasons": sorted(self.reasons)}
+
+
+def bus_id(torch, dev):
+    p = torch.cuda.get_device_properties(dev)
+    try:
+        return "%08x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+    except AttributeError:
+        return None
 
 
 def capture_records(clips, tmpdir):
@@ -226,7 +281,7 @@ def run_b200(args):
     for i in range(W, W + first):
         step(i)
     barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, bus_id(torch, local_rank))
     sampler.start()
     sync_all()
     l0 = sum(gc[0].launch_count() for gc in gctx)
