@@ -35,13 +35,21 @@
 #ifndef INTRA_SLEEP
 #define INTRA_SLEEP 32
 #endif
+/* shared-memory accesses by 32-bit shared-space address (no generic pointer to rebuild inside a
+ * register-capped loop) */
+__device__ __forceinline__ int lds_u8(unsigned a) { int v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_u8(unsigned a, int v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint2 lds_v2(unsigned a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
+
 #define YS 48             /* luma tile pitch: rows -1..15, cols -16..31 ; index (r+1)*48 + 16 + c */
 #define CS 16             /* chroma tile pitch: rows -1..7, cols -4..11 ; index (r+1)*16 + 4 + c  */
 
 /* B_PRED predictor table: [mode][pixel] = i0 | i1<<4 | i2<<8 | kind<<12 over the edge array
  * E[0..3] = L3 L2 L1 L0, E[4] = top-left, E[5..12] = A0..A7.
- * kind 0: (E[i0] + 2 E[i1] + E[i2] + 2) >> 2 ; 1: (E[i0] + E[i1] + 1) >> 1 ; 2: DC ;
- * 3: TM = clamp(E[i0] - E[i1] + E[i2]) with (i0, i1, i2) = (above, top-left, left) */
+ * kind 0: (E[i0] + 2 E[i1] + E[i2] + 2) >> 2, which with i2 = i0 is also the 2-tap average
+ * (E[i0] + E[i1] + 1) >> 1 ; 2: DC ; 3: TM = clamp(E[i0] - E[i1] + E[i2]) with
+ * (i0, i1, i2) = (above, top-left, left).  Kinds 0 and 3 are one formula,
+ * clamp((E[i0] + w E[i1] + E[i2] + s) >> s) with (w, s) = (2, 2) or (-1, 0): no divergent code. */
 __constant__ unsigned short c_bpred[10][16];
 
 static unsigned short ent(int kind, int a, int b, int c) { return (unsigned short)(a | (b << 4) | (c << 8) | (kind << 12)); }
@@ -50,7 +58,7 @@ void vp8b200_upload_intra_constants()
 {
     unsigned short t[10][16];
     auto A3 = [](int a, int b, int c) { return ent(0, a, b, c); };
-    auto A2 = [](int a, int b) { return ent(1, a, b, 0); };
+    auto A2 = [](int a, int b) { return ent(0, a, b, a); };   /* (a + b + 1) >> 1 == (a + 2b + a + 2) >> 2 */
     for (int r = 0; r < 4; r++)
         for (int c = 0; c < 4; c++) {
             const int p = r * 4 + c;
@@ -132,6 +140,21 @@ __device__ __forceinline__ void block_mode(int mode, const uint8_t *T, int ts, i
     }
 }
 
+#ifdef INTRA_PROF
+/* phase clocks of B_PRED macroblocks (variant builds only): [0] wait, [1] scatter, [2] predict,
+ * [3] export, [4] count */
+__device__ unsigned long long g_intra_prof[8];
+extern "C" void vp8b200_debug_intra_prof(unsigned long long *out)
+{
+    static const unsigned long long zero[8] = {0};
+    cudaMemcpyFromSymbol(out, g_intra_prof, sizeof zero);
+    cudaMemcpyToSymbol(g_intra_prof, zero, sizeof zero);
+}
+#define IPROF(i) do { if (phase == 0 && bpred && lane == 0) { const long long now_ = clock64(); atomicAdd(&g_intra_prof[i], (unsigned long long)(now_ - prof_t)); prof_t = now_; } } while (0)
+#else
+#define IPROF(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(INTRA_WARPS * 32, INTRA_MIN_CTAS)
 k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const unsigned max_intra,
         unsigned *ticket, const unsigned ticket_base)
@@ -140,7 +163,7 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
     __shared__ unsigned s_ticket;
     __shared__ __align__(16) uint8_t s_yt[INTRA_WARPS][17 * YS];
     __shared__ __align__(16) uint8_t s_ct[INTRA_WARPS][2][9 * CS];
-    __shared__ __align__(16) short s_res[INTRA_WARPS][16][16];
+    __shared__ __align__(16) short s_res[INTRA_WARPS][24][16];   /* residuals parked until their phase (16 registers less across the wait) */
     __shared__ uint8_t s_modes[INTRA_WARPS][16];
     /* B_PRED, per step and lane: .x = table entry | residual << 16, .y = tile offset of the
      * lane's edge element | tile offset of its pixel << 16 (0xffff: lane idle in this step) */
@@ -176,13 +199,22 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
     int res[16];
     bool has_res = false;
     if (lane < 24) has_res = block_residual(job, mb, lane, !bpred, res);
-    if (bpred && lane < 16) {
+    if (lane < 24) {                                     /* parked in shared memory until the block is predicted */
         uint4 *o = reinterpret_cast<uint4 *>(s_res[warp][lane]);
         o[0] = make_uint4((res[0] & 0xffff) | (res[1] << 16), (res[2] & 0xffff) | (res[3] << 16),
                           (res[4] & 0xffff) | (res[5] << 16), (res[6] & 0xffff) | (res[7] << 16));
         o[1] = make_uint4((res[8] & 0xffff) | (res[9] << 16), (res[10] & 0xffff) | (res[11] << 16),
                           (res[12] & 0xffff) | (res[13] << 16), (res[14] & 0xffff) | (res[15] << 16));
     }
+    auto add_parked = [&](unsigned (&px)[4]) {
+        int cr[16];
+        const uint4 *q = reinterpret_cast<const uint4 *>(s_res[warp][lane]);
+        const uint4 q0 = q[0], q1 = q[1];
+        const unsigned qw[8] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w };
+#pragma unroll
+        for (int i = 0; i < 8; i++) { cr[2 * i] = (short)(qw[i] & 0xffff); cr[2 * i + 1] = (int)qw[i] >> 16; }
+        add_res(px, cr);
+    };
     if (bpred && lane < 16) s_modes[warp][lane] = reinterpret_cast<const uint8_t *>(job.aux + mb.u.aux)[lane];
     const int pix = lane & 15, pr = pix >> 2, pc = pix & 3, which = lane >> 4;
     /* B_PRED runs its 16 sub-blocks as a 10-step anti-diagonal wavefront (block (br,bc) at step
@@ -207,8 +239,9 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
             /* column 3 takes its above-right from row -1 of the MB (reconintra4x4.c:305-317) */
             const int ld_off = (act && e >= 9 && bc == 3) ? -YS + 16 + e - 9 : b_off + e_off;
             const int st_off = act ? b_off + pr * YS + pc : 0xffff;
+            const unsigned ent = s_bpred[s_modes[warp][blk] * 16 + pix];
             s_pre[warp][step][lane] = make_uint2(
-                s_bpred[s_modes[warp][blk] * 16 + pix] | ((unsigned)(unsigned short)s_res[warp][blk][pix] << 16),
+                ent | ((unsigned)(unsigned short)s_res[warp][blk][pix] << 16),
                 (unsigned)(ld_off & 0xffff) | ((unsigned)st_off << 16));
         }
     }
@@ -235,11 +268,24 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
      * sitting on the dependency chain.  The code of a phase exists once (rolled loop: every
      * warp runs it once per macroblock, straight-line copies would only miss in the
      * instruction cache). ---- */
+    /* where this lane's border word goes in the tiles: 1 = four bytes down a column (left
+     * neighbour's words), 2 = one word of a row (above / above-right), 3 = the top-left byte */
+    uint8_t *sc_ptr = YT;
+    int sc_pitch = 0, sc_kind = 0;
+    if (lane < 4) { sc_ptr = YT + 4 * lane * YS - 1; sc_pitch = YS; sc_kind = 1; }
+    else if (lane < 8) { sc_ptr = (lane < 6 ? UT : VT) + 4 * (lane & 1) * CS - 1; sc_pitch = CS; sc_kind = 1; }
+    else if (lane < 12) { sc_ptr = YT - YS + 4 * (lane - 8); sc_kind = 2; }
+    else if (lane < 16) { sc_ptr = (lane < 14 ? UT : VT) - CS + 4 * (lane & 1); sc_kind = 2; }
+    else if (lane < 19) { sc_ptr = lane == 16 ? YT - YS - 1 : (lane == 17 ? UT : VT) - CS - 1; sc_kind = 3; }
+    else if (lane == 19) { sc_ptr = YT - YS + 16; sc_kind = 2; }
     const unsigned long long *msg = job.intra_msg;
     const bool luma_lane = lane < 4 || (lane >= 8 && lane < 12) || lane == 16 || lane == 19;
 #pragma unroll 1
     for (int phase = 0; phase < 2; phase++) {
         unsigned w = 0;
+#ifdef INTRA_PROF
+        long long prof_t = clock64();
+#endif
         if (lane < 20 && luma_lane == (phase == 0)) {
             /* which neighbour this lane reads, which word of its export, or which frame bytes */
             const int grp = lane < 8 ? 0 : (lane < 16 ? 1 : (lane < 19 ? 2 : 3));   /* left, above, above-left, above-right */
@@ -282,34 +328,31 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
                 }
             }
         }
+#ifdef INTRA_PROF
+        __syncwarp();
+        IPROF(0);
+#endif
         if (phase == 0) {
             /* above-right of the last MB column: replicate the last pixel of the above row */
             const unsigned w11 = __shfl_sync(FULL_MASK, w, 11);
             if (lane == 19 && up && !right) w = (w11 >> 24) * 0x01010101u;
         }
-        /* scatter into the tiles */
-        if (lane < 20 && luma_lane == (phase == 0)) {
-            if (lane < 4) {
-#pragma unroll
-                for (int i = 0; i < 4; i++) YT[(4 * lane + i) * YS - 1] = (uint8_t)(w >> (8 * i));
-            } else if (lane < 8) {
-                uint8_t *CT = lane < 6 ? UT : VT;
-#pragma unroll
-                for (int i = 0; i < 4; i++) CT[(4 * (lane & 1) + i) * CS - 1] = (uint8_t)(w >> (8 * i));
-            } else if (lane < 12) {
-                *reinterpret_cast<unsigned *>(YT - YS + 4 * (lane - 8)) = w;
-            } else if (lane < 16) {
-                *reinterpret_cast<unsigned *>((lane < 14 ? UT : VT) - CS + 4 * (lane & 1)) = w;
-            } else if (lane < 19) {
-                uint8_t *T = lane == 16 ? YT : (lane == 17 ? UT : VT);
-                T[-(lane == 16 ? YS : CS) - 1] = (uint8_t)(w >> 24);
-            } else {
-                *reinterpret_cast<unsigned *>(YT - YS + 16) = w;
+        /* scatter into the tiles: per-lane pointer and shape were set up before the wait, so
+         * that what follows the wait is a handful of predicated stores, not a six-way branch */
+        {
+            const bool mine = lane < 20 && luma_lane == (phase == 0);
+            if (mine && sc_kind == 2) *reinterpret_cast<unsigned *>(sc_ptr) = w;
+            if (mine && sc_kind != 2) sc_ptr[0] = (uint8_t)(sc_kind == 3 ? w >> 24 : w);
+            if (mine && sc_kind == 1) {
+                sc_ptr[sc_pitch] = (uint8_t)(w >> 8);
+                sc_ptr[2 * sc_pitch] = (uint8_t)(w >> 16);
+                sc_ptr[3 * sc_pitch] = (uint8_t)(w >> 24);
             }
         }
         __syncwarp();
         /* ---- DC value (reconintra.c:167-195, :434-462) when this phase's mode is DC_PRED:
          * lanes 0-15 sum luma, 16-23 U, 24-31 V ---- */
+        IPROF(1);
         int dc = 128;
         if ((phase == 0 ? (!bpred && mb.y_mode == VP8B200_DC_PRED) : mb.uv_mode == VP8B200_DC_PRED) && (up || left)) {
             const uint8_t *T = lane < 16 ? YT : (lane < 24 ? UT : VT);
@@ -333,35 +376,47 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
                     const int bx = (lane & 3) * 4, by = (lane >> 2) * 4;
                     unsigned px[4];
                     block_mode(mb.y_mode, YT, YS, bx, by, dc, px);
-                    if (has_res) add_res(px, res);
+                    if (has_res) add_parked(px);
                     store4x4(dy + by * g.y_stride + bx, g.y_stride, px);
                     store4x4(YT + by * YS + bx, YS, px);              /* for the export below */
                 }
             } else {
                 /* Per step one shared-memory load per lane - lane p of a block fetches element p
                  * of the block's edge array - then the three taps of the lane's pixel come from
-                 * the other lanes by shuffle.  No divergent code on the dependency chain. */
+                 * the other lanes by shuffle.  The step's dependent chain is kept to: edge load,
+                 * shuffle, four integer operations, store, warp barrier.  Everything else is
+                 * off it: the table entry of the NEXT step is fetched (and its lane numbers,
+                 * offsets and residual unpacked) while this step's edge load is in flight, and
+                 * the B_DC_PRED mean of both blocks comes from ONE warp reduction of the edge
+                 * values packed 16 bits per block, issued next to the shuffles in every step (a
+                 * uniform branch around it for steps without such a block made the loop 60 %
+                 * slower; it was a vote plus four dependent shuffles before). */
                 const bool e_dc = pix < 4 || (pix >= 5 && pix < 9);
                 const int half = lane & 16;
+                const unsigned yt_s = (unsigned)__cvta_generic_to_shared(YT);
+                unsigned pre_s = (unsigned)__cvta_generic_to_shared(&s_pre[warp][0][lane]);
+                uint2 t = lds_v2(pre_s);
 #pragma unroll 1
                 for (int step = 0; step < 10; step++) {
-                    const uint2 t = s_pre[warp][step][lane];
-                    const int edge = YT[(short)(t.y & 0xffff)];
-                    const int ea = __shfl_sync(FULL_MASK, edge, half + (t.x & 15));
-                    const int eb = __shfl_sync(FULL_MASK, edge, half + ((t.x >> 4) & 15));
-                    const int ec = __shfl_sync(FULL_MASK, edge, half + ((t.x >> 8) & 15));
+                    const int edge = lds_u8(yt_s + (short)(t.y & 0xffff));
+                    const int la = half + (t.x & 15), lb = half + ((t.x >> 4) & 15), lc = half + ((t.x >> 8) & 15);
                     const int kind = (t.x >> 12) & 3;
-                    int v = kind == 0 ? (ea + 2 * eb + ec + 2) >> 2 : (kind == 1 ? (ea + eb + 1) >> 1 : clamp255(ea - eb + ec));
-                    if (__any_sync(FULL_MASK, kind == 2)) {          /* B_DC_PRED: mean of L0..L3, A0..A3 */
-                        int sum = e_dc ? edge : 0;
-                        sum += __shfl_xor_sync(FULL_MASK, sum, 1);
-                        sum += __shfl_xor_sync(FULL_MASK, sum, 2);
-                        sum += __shfl_xor_sync(FULL_MASK, sum, 4);
-                        sum += __shfl_xor_sync(FULL_MASK, sum, 8);
-                        if (kind == 2) v = (sum + 4) >> 3;
+                    const int wb = kind == 3 ? -1 : 2, rs = kind == 3 ? 0 : 2;
+                    const int res_px = (short)(t.x >> 16);
+                    const unsigned st = t.y >> 16;
+                    if (step < 9) pre_s += 32 * sizeof(uint2);
+                    t = lds_v2(pre_s);
+                    const int ea = __shfl_sync(FULL_MASK, edge, la);
+                    const int eb = __shfl_sync(FULL_MASK, edge, lb);
+                    const int ec = __shfl_sync(FULL_MASK, edge, lc);
+                    int v = clamp255((ea + wb * eb + ec + rs) >> rs);
+                    {
+                        const unsigned sums = __reduce_add_sync(FULL_MASK, e_dc ? (unsigned)edge << half : 0u);
+                        const int dcv = (int)(((sums >> half) & 0xffffu) + 4) >> 3;
+                        v = kind == 2 ? dcv : v;
                     }
-                    v = clamp255(v + (short)(t.x >> 16));
-                    if ((t.y >> 16) != 0xffff) YT[t.y >> 16] = (uint8_t)v;
+                    v = clamp255(v + res_px);
+                    if (st != 0xffff) sts_u8(yt_s + st, v);
                     __syncwarp();
                 }
             }
@@ -370,12 +425,13 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
             const int j = lane & 3, bx = (j & 1) * 4, by = (j >> 1) * 4;
             unsigned px[4];
             block_mode(mb.uv_mode, lane < 20 ? UT : VT, CS, bx, by, dc, px);
-            if (has_res) add_res(px, res);
+            if (has_res) add_parked(px);
             store4x4((lane < 20 ? du : dv) + by * g.uv_stride + bx, g.uv_stride, px);
             store4x4((lane < 20 ? UT : VT) + by * CS + bx, CS, px);   /* for the export below */
         }
         /* ---- export this plane's bottom row + right column for the neighbours still to come ---- */
         __syncwarp();
+        IPROF(2);
         if (lane < 16 && ((lane & 4) != 0) == (phase == 1)) {
             unsigned x;
             if (lane < 4) x = *reinterpret_cast<const unsigned *>(YT + 15 * YS + 4 * lane);
@@ -391,6 +447,11 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
             unsigned long long *p = job.intra_msg + (size_t)mbi * 16 + lane;
             asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
         }
+#ifdef INTRA_PROF
+        __syncwarp();
+        IPROF(3);
+        if (phase == 0 && bpred && lane == 0) atomicAdd(&g_intra_prof[4], 1ull);
+#endif
         /* the finished B_PRED 16x16 goes out row by row, after the hand-off */
         if (phase == 0 && bpred && lane < 16) {
             const unsigned *r = reinterpret_cast<const unsigned *>(YT + lane * YS);
