@@ -14,7 +14,10 @@
  * dependency belongs to an earlier ticket, i.e. to a warp that is already running: no
  * deadlock, and no reliance on block scheduling order.  A warp waits only for those of its
  * four neighbours that are themselves intra, by polling the tagged border words they export
- * (no flags, no fences).
+ * (no flags, no fences).  The polling loop is left by the WARP as a whole (__all_sync): lanes
+ * that break out one by one leave the warp diverged, and everything after the wait - the
+ * dependency chain - then runs its shuffles through the divergent-warp fallback, several times
+ * slower (measured: profiles/r02_summary.md).
  *
  * Inside a macroblock: borders are gathered into a shared-memory tile (frame-edge values are
  * synthesised, never read from the frame), residuals of all blocks are computed first
@@ -140,20 +143,6 @@ __device__ __forceinline__ void block_mode(int mode, const uint8_t *T, int ts, i
     }
 }
 
-#ifdef INTRA_PROF
-/* phase clocks of B_PRED macroblocks (variant builds only): [0] wait, [1] scatter, [2] predict,
- * [3] export, [4] count */
-__device__ unsigned long long g_intra_prof[8];
-extern "C" void vp8b200_debug_intra_prof(unsigned long long *out)
-{
-    static const unsigned long long zero[8] = {0};
-    cudaMemcpyFromSymbol(out, g_intra_prof, sizeof zero);
-    cudaMemcpyToSymbol(g_intra_prof, zero, sizeof zero);
-}
-#define IPROF(i) do { if (phase == 0 && bpred && lane == 0) { const long long now_ = clock64(); atomicAdd(&g_intra_prof[i], (unsigned long long)(now_ - prof_t)); prof_t = now_; } } while (0)
-#else
-#define IPROF(i) do { } while (0)
-#endif
 
 __global__ void __launch_bounds__(INTRA_WARPS * 32, INTRA_MIN_CTAS)
 k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const unsigned max_intra,
@@ -283,9 +272,7 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
 #pragma unroll 1
     for (int phase = 0; phase < 2; phase++) {
         unsigned w = 0;
-#ifdef INTRA_PROF
-        long long prof_t = clock64();
-#endif
+        const unsigned long long *pp = nullptr;
         if (lane < 20 && luma_lane == (phase == 0)) {
             /* which neighbour this lane reads, which word of its export, or which frame bytes */
             const int grp = lane < 8 ? 0 : (lane < 16 ? 1 : (lane < 19 ? 2 : 3));   /* left, above, above-left, above-right */
@@ -305,14 +292,7 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
                 const bool n_intra = ((__ldg(reinterpret_cast<const unsigned *>(job.mb + ni)) >> 16) & 0xff) == VP8B200_INTRA_FRAME;
                 if (n_intra) {
                     const int word = grp == 0 ? 8 + j : (grp == 1 ? j : (grp == 2 ? 3 + 2 * j : 0));
-                    const unsigned long long *p = msg + (size_t)ni * 16 + word;
-                    unsigned long long v;
-                    for (int tries = 0;; tries++) {
-                        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-                        if ((unsigned)(v >> 32) == epoch) break;
-                        if (tries > INTRA_SPIN) __nanosleep(INTRA_SLEEP);   /* poll hard first: the hand-off is on the chain */
-                    }
-                    w = (unsigned)v;
+                    pp = msg + (size_t)ni * 16 + word;
                 } else if (grp == 0) {
                     /* 4 pixels of the column left of the MB: rows 4*jj .. 4*jj+3 of plane pl */
                     const int jj = pl == 0 ? j : (j & 1);
@@ -328,10 +308,21 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
                 }
             }
         }
-#ifdef INTRA_PROF
-        __syncwarp();
-        IPROF(0);
-#endif
+        {
+            /* every lane that has a tagged word polls it (hard first: the hand-off is on the
+             * chain); the WARP leaves the loop together */
+            unsigned long long v = 0;
+            bool ok = pp == nullptr;
+            for (int tries = 0;; tries++) {
+                if (!ok) {
+                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(pp) : "memory");
+                    ok = (unsigned)(v >> 32) == epoch;
+                }
+                if (__all_sync(FULL_MASK, ok)) break;
+                if (tries > INTRA_SPIN) __nanosleep(INTRA_SLEEP);
+            }
+            if (pp) w = (unsigned)v;
+        }
         if (phase == 0) {
             /* above-right of the last MB column: replicate the last pixel of the above row */
             const unsigned w11 = __shfl_sync(FULL_MASK, w, 11);
@@ -352,7 +343,6 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
         __syncwarp();
         /* ---- DC value (reconintra.c:167-195, :434-462) when this phase's mode is DC_PRED:
          * lanes 0-15 sum luma, 16-23 U, 24-31 V ---- */
-        IPROF(1);
         int dc = 128;
         if ((phase == 0 ? (!bpred && mb.y_mode == VP8B200_DC_PRED) : mb.uv_mode == VP8B200_DC_PRED) && (up || left)) {
             const uint8_t *T = lane < 16 ? YT : (lane < 24 ? UT : VT);
@@ -431,7 +421,6 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
         }
         /* ---- export this plane's bottom row + right column for the neighbours still to come ---- */
         __syncwarp();
-        IPROF(2);
         if (lane < 16 && ((lane & 4) != 0) == (phase == 1)) {
             unsigned x;
             if (lane < 4) x = *reinterpret_cast<const unsigned *>(YT + 15 * YS + 4 * lane);
@@ -447,11 +436,6 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
             unsigned long long *p = job.intra_msg + (size_t)mbi * 16 + lane;
             asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
         }
-#ifdef INTRA_PROF
-        __syncwarp();
-        IPROF(3);
-        if (phase == 0 && bpred && lane == 0) atomicAdd(&g_intra_prof[4], 1ull);
-#endif
         /* the finished B_PRED 16x16 goes out row by row, after the hand-off */
         if (phase == 0 && bpred && lane < 16) {
             const unsigned *r = reinterpret_cast<const unsigned *>(YT + lane * YS);

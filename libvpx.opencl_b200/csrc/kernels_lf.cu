@@ -136,6 +136,9 @@ __device__ __forceinline__ void edge8(int &p3, int &p2, int &p1, int &p0, int &q
 #ifndef LF_MIN_CTAS
 #define LF_MIN_CTAS 4
 #endif
+#ifndef LF_UNIFORM_POLL
+#define LF_UNIFORM_POLL 1
+#endif
 #ifndef LF_POLL_SLEEP
 #define LF_POLL_SLEEP 100         /* ns between polls of a global message after 8 immediate tries */
 #endif
@@ -166,19 +169,33 @@ __device__ __forceinline__ void g_load(const uint8_t *slot, unsigned long long (
     ld_msg2(slot, w[0], w[1]);
     if (luma) ld_msg2(slot + 16, w[2], w[3]);
 }
-__device__ __forceinline__ void g_recv(const uint8_t *slot, unsigned long long (&w)[4], unsigned (&m)[4], unsigned tag, bool luma)
+__device__ __forceinline__ void g_recv(const uint8_t *slot, unsigned long long (&w)[4], unsigned (&m)[4], unsigned tag, bool luma,
+                                       bool receiver)
 {
+#if LF_UNIFORM_POLL
+    /* the WARP leaves the loop together: lanes that break out one by one leave it diverged */
     int tries = 0;
     for (;;) {
-        bool ok = (unsigned)(w[0] >> 32) == tag && (unsigned)(w[1] >> 32) == tag;
-        if (luma) ok = ok && (unsigned)(w[2] >> 32) == tag && (unsigned)(w[3] >> 32) == tag;
-        if (ok) break;
+        bool ok = !receiver || ((unsigned)(w[0] >> 32) == tag && (unsigned)(w[1] >> 32) == tag);
+        if (luma && receiver) ok = ok && (unsigned)(w[2] >> 32) == tag && (unsigned)(w[3] >> 32) == tag;
+        if (__all_sync(0xffffffffu, ok)) break;
         if (++tries > 8) __nanosleep(LF_POLL_SLEEP);
-        g_load(slot, w, luma);
+        if (!ok) g_load(slot, w, luma);
     }
+#else
+    if (receiver) {
+        int tries = 0;
+        for (;;) {
+            bool ok = (unsigned)(w[0] >> 32) == tag && (unsigned)(w[1] >> 32) == tag;
+            if (luma) ok = ok && (unsigned)(w[2] >> 32) == tag && (unsigned)(w[3] >> 32) == tag;
+            if (ok) break;
+            if (++tries > 8) __nanosleep(LF_POLL_SLEEP);
+            g_load(slot, w, luma);
+        }
+    }
+#endif
     m[0] = (unsigned)w[0]; m[1] = (unsigned)w[1]; m[2] = (unsigned)w[2]; m[3] = (unsigned)w[3];
 }
-
 
 /* mode_lf_lut, loopfilter.c:52-63, two bits per y_mode: DC,V,H,TM,ZEROMV -> 1 ; B_PRED -> 0 ;
  * NEARESTMV,NEARMV,NEWMV -> 2 ; SPLITMV -> 3 */
@@ -352,11 +369,13 @@ __device__ __forceinline__ void lf_row(const FrameJob &job, const Geo &g, const 
                 }
                 __syncwarp();
                 if (lane == 0) s_rcvd[warp - 1] = (unsigned)c + 1;
-            } else if (receiver) {
+            } else {
                 unsigned m[4];
-                g_recv(gmsg_in + (size_t)c * 256, gw, m, tag, luma);
-                if (c + 1 < g.mb_cols) g_load(gmsg_in + (size_t)(c + 1) * 256, gw, luma);
-                *reinterpret_cast<uint4 *>(tile + pi * 16) = make_uint4(m[0], m[1], m[2], m[3]);
+                g_recv(gmsg_in + (size_t)c * 256, gw, m, tag, luma, receiver);
+                if (receiver) {
+                    if (c + 1 < g.mb_cols) g_load(gmsg_in + (size_t)(c + 1) * 256, gw, luma);
+                    *reinterpret_cast<uint4 *>(tile + pi * 16) = make_uint4(m[0], m[1], m[2], m[3]);
+                }
             }
         }
         {

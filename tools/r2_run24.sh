@@ -1,0 +1,4 @@
+O=gpurun_out/r2w; mkdir -p $O
+export VP8B200_LIB=$PWD/gpurun_variants_iprof.so
+timeout 300 python tools/kernel_times.py --streams 1 --frames 2 --reps 3 > $O/kt1.txt 2>&1; grep -A2 "^frame  0" $O/kt1.txt | cut -c1-160
+timeout 300 python tools/kernel_times.py --streams 64 --frames 2 --reps 3 > $O/kt64.txt 2>&1; grep -A2 "^frame  0" $O/kt64.txt | cut -c1-160

@@ -1,0 +1,8 @@
+O=gpurun_out/r2ao; mkdir -p $O
+export VP8B200_LIB=$PWD/gpurun_variants_oldu.so
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_kat.py -q -x --timeout 120 > $O/tests_quick.log 2>&1; echo "oldu quick tests rc=$? $(tail -1 $O/tests_quick.log)"
+for v in base oldu head; do
+  if [ $v = base ]; then unset VP8B200_LIB; else export VP8B200_LIB=$PWD/gpurun_variants_$v.so; fi
+  timeout 300 python tools/kernel_times.py --streams 1 --frames 2 --reps 3 > $O/kt1_$v.txt 2>&1; echo "$v 1 stream: $(grep '^frame  0' $O/kt1_$v.txt | cut -c60-110)"
+  timeout 300 python tools/kernel_times.py --streams 64 --frames 30 --reps 2 > $O/kt64_$v.txt 2>&1; grep "^frame" $O/kt64_$v.txt | awk '{k+= ($4==0)? $16:0; if ($4==1) s+=$16} END {print "   64 streams: key", k, "P total", s}'
+done
