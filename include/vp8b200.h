@@ -190,7 +190,9 @@ int vp8b200_frame_fetch(vp8b200_ctx *ctx, int fb, uint8_t *dst, size_t bytes);
  * YV12 mirror, buffer_alloc): with display_w/h > 0 only the visible samples are copied
  * (display_w x display_h luma, ((w+1)/2) x ((h+1)/2) chroma - what vpx_codec_get_frame's
  * caller may read, vpxdec.c:1093-1115), each to the offset it has in the allocation;
- * display_w == display_h == 0 copies the whole allocation, borders included. */
+ * display_w == display_h == 0 copies the whole allocation, borders included.  Up to two copies
+ * may be in flight per context; fetch_wait collects the OLDEST one (frame-delay mode queues
+ * picture N before it collects picture N-1), a third fetch_begin first waits for the oldest. */
 int vp8b200_frame_fetch_begin(vp8b200_ctx *ctx, int fb, uint8_t *dst, int display_w, int display_h);
 int vp8b200_frame_fetch_wait(vp8b200_ctx *ctx);
 /* Upload a whole frame buffer (VP8_SET_REFERENCE, onyxd_if.c:161-230). */

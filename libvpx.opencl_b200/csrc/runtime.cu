@@ -81,11 +81,15 @@ struct vp8b200_ctx {
     uint64_t launches;
     bool blocking_sync;            /* VP8B200_SYNC=block: sleep instead of spinning in fetch */
     /* lazy device->host fetch: the copy is queued on its own stream behind
-     * recon_done (recorded on the launch stream), fetch_done fires when the pixels are in host
-     * memory.  fetch_fb >= 0 while a copy may still be reading that device buffer. */
+     * recon_done (recorded on the launch stream); its event fires when the pixels are in host
+     * memory.  Up to two copies are in flight per context, oldest first (frame-delay mode
+     * collects picture N-1 after picture N has been queued): fetch[i].fb >= 0 while that copy
+     * may still be reading the device buffer, .seq != 0 when the ENGINE thread records the
+     * event while issuing the submit with that sequence number. */
     cudaStream_t copy_stream;
-    cudaEvent_t recon_done, fetch_done;
-    int fetch_fb;
+    cudaEvent_t recon_done;
+    struct { cudaEvent_t ev; int fb; uint32_t seq; } fetch[2];
+    int fetch_head, fetch_n;
     bool profiling, prof_skip;
     std::vector<ProfSpan> *spans;
     /* cross-stream ordering between a context's own stream and a batch leader's stream */
@@ -129,6 +133,7 @@ struct EngineSubmit {
     vp8b200_frame_hdr hdr;
     uint64_t seq;
     int show_fb;                   /* < 0: not shown */
+    int show_rec;                  /* which of the context's two fetch records tracks the copy */
     uint8_t *show_dst;
     int show_w, show_h;
 };
@@ -212,7 +217,8 @@ static void free_ctx(vp8b200_ctx *c)
     if (c->batch_pending) cudaEventSynchronize(c->batch_ev);   /* a batch on another leader's stream may still use us */
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
-    if (c->fetch_done) cudaEventSynchronize(c->fetch_done);    /* a copy queued by the engine on its own copy stream */
+    for (int i = 0; i < 2; i++)                                 /* copies queued by the engine on its own copy stream */
+        if (c->fetch[i].ev && c->fetch[i].fb >= 0) cudaEventSynchronize(c->fetch[i].ev);
     {
         /* every batch this context led has finished now: members need not (and, once the
          * events below are destroyed, must not) wait for them any more */
@@ -237,7 +243,7 @@ static void free_ctx(vp8b200_ctx *c)
     if (c->own_ev) cudaEventDestroy(c->own_ev);
     cudaFree(c->d_imsg); cudaFree(c->d_diag); cudaFree(c->d_tickets); cudaFree(c->d_lfmsg);
     free(c->diag_tmp);
-    if (c->fetch_done) cudaEventDestroy(c->fetch_done);
+    for (int i = 0; i < 2; i++) if (c->fetch[i].ev) cudaEventDestroy(c->fetch[i].ev);
     if (c->recon_done) cudaEventDestroy(c->recon_done);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->spans) {
@@ -278,7 +284,8 @@ static int create_impl(vp8b200_ctx *c)
     CK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CK(c, cudaEventCreateWithFlags(&c->recon_done, cudaEventDisableTiming));
-    c->fetch_fb = -1;
+    c->fetch[0].fb = c->fetch[1].fb = -1;
+    c->fetch_head = c->fetch_n = 0;
     vp8b200_upload_constants();
     vp8b200_upload_intra_constants();
     CK(c, cudaGetLastError());
@@ -327,8 +334,9 @@ static int create_impl(vp8b200_ctx *c)
     {
         const char *e = getenv("VP8B200_SYNC");
         c->blocking_sync = e && !strcmp(e, "block");
-        CK(c, cudaEventCreateWithFlags(&c->fetch_done, cudaEventDisableTiming |
-                                       (c->blocking_sync ? cudaEventBlockingSync : 0)));
+        for (int i = 0; i < 2; i++)
+            CK(c, cudaEventCreateWithFlags(&c->fetch[i].ev, cudaEventDisableTiming |
+                                           (c->blocking_sync ? cudaEventBlockingSync : 0)));
     }
     CK(c, cudaStreamSynchronize(c->stream));
     return VP8B200_OK;
@@ -396,10 +404,9 @@ static int join_batch(vp8b200_ctx *c)
  * WRITE that buffer (on stream `s`) behind it.  Reads need no ordering. */
 static int order_after_fetch(vp8b200_ctx *c, cudaStream_t s, int fb)
 {
-    if (c->fetch_fb >= 0 && c->fetch_fb == fb) {
-        CK(c, cudaStreamWaitEvent(s, c->fetch_done, 0));
-        c->fetch_fb = -1;
-    }
+    for (int i = 0; i < 2; i++)
+        if (__atomic_load_n(&c->fetch[i].fb, __ATOMIC_RELAXED) == fb && fb >= 0)
+            CK(c, cudaStreamWaitEvent(s, c->fetch[i].ev, 0));
     return VP8B200_OK;
 }
 
@@ -661,6 +668,46 @@ static void engine_settle(vp8b200_ctx *c)
     }
 }
 
+/* wait until the engine thread has issued this context's submit number `seq` */
+static void engine_wait_seq(vp8b200_ctx *c, uint32_t seq)
+{
+    if (!c->eng) return;
+    for (;;) {
+        const uint32_t have = __atomic_load_n(&c->eng_issued, __ATOMIC_ACQUIRE);
+        if ((int32_t)(have - seq) >= 0) return;
+        syscall(SYS_futex, &c->eng_issued, FUTEX_WAIT_PRIVATE, have, NULL, NULL, 0);
+    }
+}
+
+/* the oldest copy in flight is in host memory */
+static int fetch_retire_oldest(vp8b200_ctx *c)
+{
+    if (c->fetch_n == 0) return VP8B200_OK;
+    const int i = c->fetch_head;
+    if (c->fetch[i].seq) engine_wait_seq(c, c->fetch[i].seq);   /* its event is recorded by the engine thread */
+    c->fetch_head = (i + 1) & 1;
+    c->fetch_n--;
+    if (c->eng_status) { __atomic_store_n(&c->fetch[i].fb, -1, __ATOMIC_RELAXED); int st = c->eng_status; c->eng_status = 0; return st; }
+    CK(c, cudaSetDevice(c->device));
+    cudaError_t e = cudaEventSynchronize(c->fetch[i].ev);
+    __atomic_store_n(&c->fetch[i].fb, -1, __ATOMIC_RELAXED);
+    CK(c, e);
+    return VP8B200_OK;
+}
+
+/* a record for a new copy of buffer fb (the caller never collected two older ones: the oldest is
+ * waited for here) */
+static int fetch_reserve(vp8b200_ctx *c, int fb, uint32_t seq, int *rec)
+{
+    if (c->fetch_n == 2) { int st = fetch_retire_oldest(c); if (st) return st; }
+    const int i = (c->fetch_head + c->fetch_n) & 1;
+    c->fetch[i].seq = seq;
+    __atomic_store_n(&c->fetch[i].fb, fb, __ATOMIC_RELAXED);
+    c->fetch_n++;
+    *rec = i;
+    return VP8B200_OK;
+}
+
 #define ECK(call)                                                                          \
     do {                                                                                   \
         cudaError_t e_ = (call);                                                           \
@@ -723,7 +770,9 @@ static int engine_issue(Engine *e, std::vector<EngineSubmit> &b, char (&err)[256
             ECK(cudaStreamWaitEvent(st, c->own_ev, 0));
             c->own_dirty = false;
         }
-        if (c->fetch_fb >= 0 && c->fetch_fb == h.fb_new) { ECK(cudaStreamWaitEvent(st, c->fetch_done, 0)); c->fetch_fb = -1; }
+        for (int k = 0; k < 2; k++)                            /* an OLDER copy may still be reading the buffer we write */
+            if (__atomic_load_n(&c->fetch[k].fb, __ATOMIC_RELAXED) == (int)h.fb_new && !(sb.show_fb >= 0 && k == sb.show_rec))
+                ECK(cudaStreamWaitEvent(st, c->fetch[k].ev, 0));
         if (!key && sb.n_intra)
             ECK(cudaMemcpyAsync(s.d_ilist, s.h_ilist, (size_t)sb.n_intra * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         ECK(cudaMemcpyAsync(s.d_mb, s.h_mb, (size_t)c->n_mb * sizeof(vp8b200_mb), cudaMemcpyHostToDevice, st));
@@ -777,8 +826,7 @@ static int engine_issue(Engine *e, std::vector<EngineSubmit> &b, char (&err)[256
                                       (size_t)cw, (size_t)ch, cudaMemcpyDeviceToHost, e->copy_stream));
                 g_d2h_bytes += (uint64_t)sb.show_w * sb.show_h + 2ull * cw * ch;
             }
-            ECK(cudaEventRecord(c->fetch_done, e->copy_stream));
-            c->fetch_fb = sb.show_fb;
+            ECK(cudaEventRecord(c->fetch[sb.show_rec].ev, e->copy_stream));
         }
     }
     e->batches++;
@@ -864,6 +912,11 @@ extern "C" int vp8b200_frame_submit_show(vp8b200_ctx *c, uint32_t n_aux, uint32_
         return VP8B200_ERR_INVALID;
     }
     c->cur = (c->cur + 1) % NSLOT;
+    sb.show_rec = 0;
+    if (show_fb >= 0) {
+        int st = fetch_reserve(c, show_fb, (uint32_t)(c->eng_submitted + 1), &sb.show_rec);
+        if (st) return st;
+    }
     {
         std::lock_guard<std::mutex> lk(c->eng->mu);
         sb.seq = ++c->eng_submitted;
@@ -891,12 +944,8 @@ extern "C" int vp8b200_frame_fetch_begin(vp8b200_ctx *c, int fb, uint8_t *dst, i
     engine_settle(c);
     CK(c, cudaSetDevice(c->device));
     { int js = join_batch(c); if (js) return js; }
-    if (c->fetch_fb >= 0) {
-        /* one copy is tracked per context: the previous one was never waited for (the caller
-         * skipped vpx_codec_get_frame).  Later launches simply wait for it. */
-        CK(c, cudaStreamWaitEvent(c->stream, c->fetch_done, 0));
-        c->fetch_fb = -1;
-    }
+    int rec = 0;
+    { int rs = fetch_reserve(c, fb, 0, &rec); if (rs) return rs; }
     const Geo &g = c->geo;
     CK(c, cudaEventRecord(c->recon_done, c->stream));
     CK(c, cudaStreamWaitEvent(c->copy_stream, c->recon_done, 0));
@@ -913,22 +962,24 @@ extern "C" int vp8b200_frame_fetch_begin(vp8b200_ctx *c, int fb, uint8_t *dst, i
                                 (size_t)cw, (size_t)ch, cudaMemcpyDeviceToHost, c->copy_stream));
         g_d2h_bytes += (uint64_t)display_w * display_h + 2ull * cw * ch;
     }
-    CK(c, cudaEventRecord(c->fetch_done, c->copy_stream));
-    c->fetch_fb = fb;
+    CK(c, cudaEventRecord(c->fetch[rec].ev, c->copy_stream));
     return VP8B200_OK;
 }
 
-/* Wait until the copy queued by the last fetch_begin is in host memory.  Device faults of the
- * frame's kernels surface here (or at the next call) as VP8B200_ERR_CUDA. */
+/* Wait until the OLDEST copy in flight (fetch_begin / frame_submit_show) is in host memory: up
+ * to two are tracked, so a caller in frame-delay mode collects picture N-1 while picture N is
+ * still being reconstructed.  Device faults of the frame's kernels surface here (or at the
+ * next call) as VP8B200_ERR_CUDA. */
 extern "C" int vp8b200_frame_fetch_wait(vp8b200_ctx *c)
 {
     if (!c) return VP8B200_ERR_INVALID;
-    engine_settle(c);                               /* the copy is queued by the engine thread */
-    if (c->eng_status) { int st = c->eng_status; c->eng_status = 0; return st; }
-    CK(c, cudaSetDevice(c->device));
-    CK(c, cudaEventSynchronize(c->fetch_done));
-    c->fetch_fb = -1;
-    return VP8B200_OK;
+    if (c->fetch_n == 0) {
+        /* nothing in flight: still the place where an engine failure of an unshown frame surfaces */
+        engine_settle(c);
+        if (c->eng_status) { int st = c->eng_status; c->eng_status = 0; return st; }
+        return VP8B200_OK;
+    }
+    return fetch_retire_oldest(c);
 }
 
 extern "C" int vp8b200_frame_fetch(vp8b200_ctx *c, int fb, uint8_t *dst, size_t bytes)
@@ -936,8 +987,10 @@ extern "C" int vp8b200_frame_fetch(vp8b200_ctx *c, int fb, uint8_t *dst, size_t 
     if (!c || fb < 0 || fb >= c->n_fb || !dst || bytes > c->frame_size) return VP8B200_ERR_INVALID;
     engine_settle(c);
     if (bytes == c->frame_size) {
+        /* blocking: every copy in flight, this one last, is in host memory on return */
         int st = vp8b200_frame_fetch_begin(c, fb, dst, 0, 0);
-        return st ? st : vp8b200_frame_fetch_wait(c);
+        while (!st && c->fetch_n) st = fetch_retire_oldest(c);
+        return st;
     }
     CK(c, cudaSetDevice(c->device));
     { int js = join_batch(c); if (js) return js; }
@@ -982,7 +1035,7 @@ extern "C" int vp8b200_sync(vp8b200_ctx *c)
     CK(c, cudaStreamSynchronize(c->stream));
     CK(c, cudaStreamSynchronize(c->copy_stream));
     c->own_dirty = false;
-    c->fetch_fb = -1;
+    while (c->fetch_n) { int st = fetch_retire_oldest(c); if (st) return st; }
     return VP8B200_OK;
 }
 

@@ -46,12 +46,20 @@ def test_lazy_fetch_of_the_visible_samples(gpu_lib):
         for y in range(h):
             want[off + y * stride: off + y * stride + w] = a[off + y * stride: off + y * stride + w]
     assert np.array_equal(out, want)
-    # whole allocation through the same lazy pair; a second begin before the wait is legal
-    buf1, buf2 = np.zeros(geo.frame_size, np.uint8), np.zeros(geo.frame_size, np.uint8)
+    # whole allocation through the same lazy pair; two copies may be in flight, fetch_wait
+    # collects the oldest; a third begin first waits for the oldest itself
+    buf1, buf2, buf3 = (np.zeros(geo.frame_size, np.uint8) for _ in range(3))
     assert gpu_lib.vp8b200_frame_fetch_begin(ctx.h, 1, buf1.ctypes.data_as(C.c_void_p), 0, 0) == 0
     assert gpu_lib.vp8b200_frame_fetch_begin(ctx.h, 1, buf2.ctypes.data_as(C.c_void_p), 0, 0) == 0
     assert gpu_lib.vp8b200_frame_fetch_wait(ctx.h) == 0
-    assert np.array_equal(buf1, a) and np.array_equal(buf2, a)
+    assert np.array_equal(buf1, a)
+    assert gpu_lib.vp8b200_frame_fetch_begin(ctx.h, 1, buf3.ctypes.data_as(C.c_void_p), 0, 0) == 0
+    assert gpu_lib.vp8b200_frame_fetch_begin(ctx.h, 1, buf1.ctypes.data_as(C.c_void_p), 0, 0) == 0   # third in flight
+    assert np.array_equal(buf2, a)                                # ... so the oldest was waited for
+    assert gpu_lib.vp8b200_frame_fetch_wait(ctx.h) == 0
+    assert np.array_equal(buf3, a)
+    assert gpu_lib.vp8b200_frame_fetch_wait(ctx.h) == 0
+    assert gpu_lib.vp8b200_frame_fetch_wait(ctx.h) == 0           # nothing in flight: a no-op
     assert gpu_lib.vp8b200_frame_fetch_begin(ctx.h, 1, buf1.ctypes.data_as(C.c_void_p), 65, 48) == -1   # wider than coded
     assert gpu_lib.vp8b200_frame_fetch_begin(ctx.h, 1, buf1.ctypes.data_as(C.c_void_p), 64, 0) == -1
     ctx.close()

@@ -228,6 +228,37 @@ def test_leader_destroyed_before_its_batch_members(gpu_lib):
         c.close()
 
 
+def test_two_pictures_in_flight_are_collected_oldest_first(gpu_lib):
+    """Frame-delay order at the C ABI: picture N is queued (frame_submit_show)
+    BEFORE picture N-1 is collected; fetch_wait must hand over N-1 - complete and correct - while
+    N may still be running."""
+    mb_cols, mb_rows, n_frames = 9, 6, 7
+    w, h = mb_cols * 16, mb_rows * 16
+    geo = frames.Geometry(w, h)
+    rng = np.random.default_rng(123)
+    ctx = abi.Context(w, h, 4)
+    ora = OracleDecoder(w, h, 4)
+    for fb, buf in enumerate(randrec.random_buffers(rng, geo.frame_size, 4)):
+        ctx.upload(fb, buf)
+        ora.fb(fb)[:] = buf
+    outs = [np.zeros(geo.frame_size, np.uint8) for _ in range(3)]
+    want = {}
+    # two buffers alternate as new / last: frame f writes the buffer picture f-2 was copied from
+    fbs = [0, 1, 2, 3]
+    for f in range(n_frames):
+        fr = randrec.random_frame(rng, mb_cols, mb_rows, key=(f == 0), p_intra=0.1, fbs=tuple(fbs))
+        ctx.submit_show(fr, show_fb=fbs[0], out=outs[f % 3], display=(w, h))
+        ora.frame(fr)
+        want[f] = geo.i420(ora.fb(fbs[0]), w, h)
+        if f >= 1:
+            ctx.fetch_wait()                                      # collects picture f-1
+            assert geo.i420(outs[(f - 1) % 3], w, h) == want[f - 1], f - 1
+        fbs = [fbs[1], fbs[0]] + fbs[2:]
+    ctx.fetch_wait()
+    assert geo.i420(outs[(n_frames - 1) % 3], w, h) == want[n_frames - 1]
+    ctx.close()
+
+
 def test_coalesced_submit_batches_frames_of_many_contexts(gpu_lib):
     """SURVEY 8b "shared batch scheduler across ctxs": vp8b200_frame_submit_show hands frames to
     the per-device engine, whose thread issues ONE launch of each kernel over the frames of all
