@@ -54,6 +54,9 @@ __device__ __forceinline__ uint2 lds_v2(unsigned a) { uint2 v; asm volatile("ld.
  * (i0, i1, i2) = (above, top-left, left).  Kinds 0 and 3 are one formula,
  * clamp((E[i0] + w E[i1] + E[i2] + s) >> s) with (w, s) = (2, 2) or (-1, 0): no divergent code. */
 __constant__ unsigned short c_bpred[10][16];
+/* B_PRED wavefront geometry, [step][which]: blk | active << 4 | (column 3) << 5 | tile offset of the
+ * block's pixel (0,0) << 8 */
+__constant__ unsigned c_bstep[10][2];
 
 static unsigned short ent(int kind, int a, int b, int c) { return (unsigned short)(a | (b << 4) | (c << 8) | (kind << 12)); }
 
@@ -112,6 +115,14 @@ void vp8b200_upload_intra_constants()
     S(VP8B200_B_HU_PRED, 3, 2, A3(0, 0, 0)); S(VP8B200_B_HU_PRED, 3, 3, A3(0, 0, 0));
 #undef S
     cudaMemcpyToSymbol(c_bpred, t, sizeof t);
+    unsigned st[10][2];
+    for (int step = 0; step < 10; step++)
+        for (int which = 0; which < 2; which++) {
+            const int br = (step > 3 ? (step - 2) >> 1 : 0) + which, bc = step - 2 * br;
+            const bool act = br <= 3 && bc >= 0 && bc <= 3;
+            st[step][which] = act ? (unsigned)((br * 4 + bc) | 16 | (bc == 3 ? 32 : 0) | ((br * 4 * YS + bc * 4) << 8)) : 0u;
+        }
+    cudaMemcpyToSymbol(c_bstep, st, sizeof st);
 }
 
 /* whole-block modes (reconintra.c:139-263, :403-546) for the lane's 4x4 block at (bx, by);
@@ -158,7 +169,9 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
      * lane's edge element | tile offset of its pixel << 16 (0xffff: lane idle in this step) */
     __shared__ uint2 s_pre[INTRA_WARPS][10][32];
     __shared__ unsigned short s_bpred[160];              /* per-lane indexing: shared, not constant */
-    for (int i = threadIdx.x; i < 160; i += blockDim.x) s_bpred[i] = (&c_bpred[0][0])[i];
+    __shared__ unsigned s_bstep[20];
+    for (int i = threadIdx.x; i < 160; i += INTRA_WARPS * 32) s_bpred[i] = (&c_bpred[0][0])[i];
+    if (threadIdx.x < 20) s_bstep[threadIdx.x] = (&c_bstep[0][0])[threadIdx.x];
     if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u) - ticket_base;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -219,15 +232,16 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
          * E[4] = top-left, E[5..12] = above / above-right */
         const int e = min(pix, 12);
         const int e_off = e < 4 ? (3 - e) * YS - 1 : e - 5 - YS;
+        const int ar_off = -YS + 16 + e - 9;                 /* above-right of column 3: row -1 of the MB (reconintra4x4.c:305-317) */
+        const int px_off = pr * YS + pc;
 #pragma unroll 1
         for (int step = 0; step < 10; step++) {
-            const int br = (step > 3 ? (step - 2) >> 1 : 0) + which, bc = step - 2 * br;
-            const bool act = br <= 3 && bc >= 0 && bc <= 3;
-            const int blk = act ? br * 4 + bc : 0;
-            const int b_off = act ? br * 4 * YS + bc * 4 : 0;          /* block pixel (0,0) in the tile */
-            /* column 3 takes its above-right from row -1 of the MB (reconintra4x4.c:305-317) */
-            const int ld_off = (act && e >= 9 && bc == 3) ? -YS + 16 + e - 9 : b_off + e_off;
-            const int st_off = act ? b_off + pr * YS + pc : 0xffff;
+            const unsigned sg = s_bstep[step * 2 + which];
+            const int blk = sg & 15;
+            const bool act = (sg & 16) != 0;
+            const int b_off = sg >> 8;                        /* block pixel (0,0) in the tile */
+            const int ld_off = (e >= 9 && (sg & 32)) ? ar_off : b_off + e_off;
+            const int st_off = act ? b_off + px_off : 0xffff;
             const unsigned ent = s_bpred[s_modes[warp][blk] * 16 + pix];
             s_pre[warp][step][lane] = make_uint2(
                 ent | ((unsigned)(unsigned short)s_res[warp][blk][pix] << 16),
@@ -269,45 +283,52 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
     else if (lane == 19) { sc_ptr = YT - YS + 16; sc_kind = 2; }
     const unsigned long long *msg = job.intra_msg;
     const bool luma_lane = lane < 4 || (lane >= 8 && lane < 12) || lane == 16 || lane == 19;
-#pragma unroll 1
-    for (int phase = 0; phase < 2; phase++) {
-        unsigned w = 0;
-        const unsigned long long *pp = nullptr;
-        if (lane < 20 && luma_lane == (phase == 0)) {
-            /* which neighbour this lane reads, which word of its export, or which frame bytes */
-            const int grp = lane < 8 ? 0 : (lane < 16 ? 1 : (lane < 19 ? 2 : 3));   /* left, above, above-left, above-right */
-            const bool exists = grp == 0 ? left : (up && (grp == 2 ? left : (grp == 3 ? right : true)));
-            const int ni = mbi + (grp == 0 ? -1 : (grp == 1 ? -g.mb_cols : (grp == 2 ? -g.mb_cols - 1 : -g.mb_cols + 1)));
-            const int j = grp == 0 ? lane : (grp == 1 ? lane - 8 : lane - 16);     /* index inside the group */
-            /* plane of the word: words 0-3 Y, 4-5 U, 6-7 V (both for rows and columns) */
-            const int pl = grp >= 2 ? (grp == 3 ? 0 : j) : (j < 4 ? 0 : (j < 6 ? 1 : 2));
-            const int stride = pl == 0 ? g.y_stride : g.uv_stride;
-            const uint8_t *base = pl == 0 ? dy : (pl == 1 ? du : dv);
-            const int size = pl == 0 ? 16 : 8;
-            if (!exists) {
-                /* row above the frame is 127 (incl. top-left and above-right), column left of it 129;
-                 * above-right of the last column replicates the above MB's last pixel (filled below) */
-                w = (grp == 0 || (grp == 2 && up)) ? 0x81818181u : 0x7f7f7f7fu;
+    /* Each lane < 20 has a fixed role - one border word of one neighbour - whatever the phase;
+     * everything about it is settled here, BEFORE the wait: the word's address when the
+     * neighbour is intra (pp), else its value: synthesised at the frame edge or read from the
+     * frame (inter neighbours were finished by k_inter, so those loads are off the chain too). */
+    unsigned w_fixed = 0;
+    const unsigned long long *pp_fixed = nullptr;
+    if (lane < 20) {
+        /* which neighbour this lane reads, which word of its export, or which frame bytes */
+        const int grp = lane < 8 ? 0 : (lane < 16 ? 1 : (lane < 19 ? 2 : 3));   /* left, above, above-left, above-right */
+        const bool exists = grp == 0 ? left : (up && (grp == 2 ? left : (grp == 3 ? right : true)));
+        const int ni = mbi + (grp == 0 ? -1 : (grp == 1 ? -g.mb_cols : (grp == 2 ? -g.mb_cols - 1 : -g.mb_cols + 1)));
+        const int j = grp == 0 ? lane : (grp == 1 ? lane - 8 : lane - 16);     /* index inside the group */
+        /* plane of the word: words 0-3 Y, 4-5 U, 6-7 V (both for rows and columns) */
+        const int pl = grp >= 2 ? (grp == 3 ? 0 : j) : (j < 4 ? 0 : (j < 6 ? 1 : 2));
+        const int stride = pl == 0 ? g.y_stride : g.uv_stride;
+        const uint8_t *base = pl == 0 ? dy : (pl == 1 ? du : dv);
+        const int size = pl == 0 ? 16 : 8;
+        if (!exists) {
+            /* row above the frame is 127 (incl. top-left and above-right), column left of it 129;
+             * above-right of the last column replicates the above MB's last pixel (filled below) */
+            w_fixed = (grp == 0 || (grp == 2 && up)) ? 0x81818181u : 0x7f7f7f7fu;
+        } else {
+            const bool n_intra = ((__ldg(reinterpret_cast<const unsigned *>(job.mb + ni)) >> 16) & 0xff) == VP8B200_INTRA_FRAME;
+            if (n_intra) {
+                const int word = grp == 0 ? 8 + j : (grp == 1 ? j : (grp == 2 ? 3 + 2 * j : 0));
+                pp_fixed = msg + (size_t)ni * 16 + word;
+            } else if (grp == 0) {
+                /* 4 pixels of the column left of the MB: rows 4*jj .. 4*jj+3 of plane pl */
+                const int jj = pl == 0 ? j : (j & 1);
+                const uint8_t *q = base + (size_t)(4 * jj) * stride - 1;
+                w_fixed = q[0] | (q[stride] << 8) | (q[2 * stride] << 16) | ((unsigned)q[3 * stride] << 24);
+            } else if (grp == 1) {
+                const int jj = pl == 0 ? j : (j & 1);
+                w_fixed = *reinterpret_cast<const unsigned *>(base - stride + 4 * jj);
+            } else if (grp == 2) {
+                w_fixed = (unsigned)base[-stride - 1] << 24;                  /* same byte position as in the word */
             } else {
-                const bool n_intra = ((__ldg(reinterpret_cast<const unsigned *>(job.mb + ni)) >> 16) & 0xff) == VP8B200_INTRA_FRAME;
-                if (n_intra) {
-                    const int word = grp == 0 ? 8 + j : (grp == 1 ? j : (grp == 2 ? 3 + 2 * j : 0));
-                    pp = msg + (size_t)ni * 16 + word;
-                } else if (grp == 0) {
-                    /* 4 pixels of the column left of the MB: rows 4*jj .. 4*jj+3 of plane pl */
-                    const int jj = pl == 0 ? j : (j & 1);
-                    const uint8_t *q = base + (size_t)(4 * jj) * stride - 1;
-                    w = q[0] | (q[stride] << 8) | (q[2 * stride] << 16) | ((unsigned)q[3 * stride] << 24);
-                } else if (grp == 1) {
-                    const int jj = pl == 0 ? j : (j & 1);
-                    w = *reinterpret_cast<const unsigned *>(base - stride + 4 * jj);
-                } else if (grp == 2) {
-                    w = (unsigned)base[-stride - 1] << 24;                        /* same byte position as in the word */
-                } else {
-                    w = *reinterpret_cast<const unsigned *>(base - stride + size);
-                }
+                w_fixed = *reinterpret_cast<const unsigned *>(base - stride + size);
             }
         }
+    }
+#pragma unroll 1
+    for (int phase = 0; phase < 2; phase++) {
+        const bool mine = lane < 20 && luma_lane == (phase == 0);
+        unsigned w = mine ? w_fixed : 0u;
+        const unsigned long long *pp = mine ? pp_fixed : nullptr;
         {
             /* every lane that has a tagged word polls it (hard first: the hand-off is on the
              * chain); the WARP leaves the loop together */
@@ -331,7 +352,6 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
         /* scatter into the tiles: per-lane pointer and shape were set up before the wait, so
          * that what follows the wait is a handful of predicated stores, not a six-way branch */
         {
-            const bool mine = lane < 20 && luma_lane == (phase == 0);
             if (mine && sc_kind == 2) *reinterpret_cast<unsigned *>(sc_ptr) = w;
             if (mine && sc_kind != 2) sc_ptr[0] = (uint8_t)(sc_kind == 3 ? w >> 24 : w);
             if (mine && sc_kind == 1) {

@@ -473,7 +473,7 @@ k_loopfilter(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g,
     {
         const unsigned *s = reinterpret_cast<const unsigned *>(&jobs[ji]);
         unsigned *d = reinterpret_cast<unsigned *>(&job);
-        for (int i = threadIdx.x; i < (int)(sizeof(FrameJob) / 4); i += blockDim.x) d[i] = s[i];
+        for (int i = threadIdx.x; i < (int)(sizeof(FrameJob) / 4); i += LF_ROWS_PER_CTA * 32) d[i] = s[i];
     }
     __syncthreads();
     const vp8b200_frame_hdr &h = job.hdr;

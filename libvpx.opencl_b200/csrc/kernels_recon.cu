@@ -163,7 +163,7 @@ k_inter_split(const FrameJob *__restrict__ jobs, const Geo g)
     {
         const unsigned *s = reinterpret_cast<const unsigned *>(&jobs[blockIdx.y]);
         unsigned *d = reinterpret_cast<unsigned *>(&job);
-        for (int i = threadIdx.x; i < (int)(sizeof(FrameJob) / 4); i += blockDim.x) d[i] = s[i];
+        for (int i = threadIdx.x; i < (int)(sizeof(FrameJob) / 4); i += WARPS_PER_CTA * 32) d[i] = s[i];
     }
     __syncthreads();
     if (job.hdr.frame_type == 0 || job.n_split == 0) return;   /* nothing to do in this frame */
@@ -355,7 +355,7 @@ k_inter16(const FrameJob *__restrict__ jobs, const Geo g)
     {
         const unsigned *s = reinterpret_cast<const unsigned *>(&jobs[blockIdx.y]);
         unsigned *d = reinterpret_cast<unsigned *>(&job);
-        for (int i = threadIdx.x; i < (int)(sizeof(FrameJob) / 4); i += blockDim.x) d[i] = s[i];
+        for (int i = threadIdx.x; i < (int)(sizeof(FrameJob) / 4); i += I16_WARPS * 32) d[i] = s[i];
     }
     __syncthreads();
     if (job.hdr.frame_type == 0) return;                       /* key frame: nothing inter */
