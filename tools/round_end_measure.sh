@@ -1,22 +1,12 @@
-# round-end measurement set (run under gpurun): GPU tests, smoke, e2e CPU split, both bench arms,
-# ncu launch list + one full capture of k_loopfilter, per-config table. Outputs: gpurun_out/v8/ ->
-# the ones that are evidence are copied to profiles/ by hand.
-mkdir -p gpurun_out/v8
-python -m pytest tests -m gpu -q > gpurun_out/v8/tests.log 2>&1; echo "tests rc=$? $(tail -1 gpurun_out/v8/tests.log)"
-python __graft_entry__.py smoke > gpurun_out/v8/smoke.log 2>&1; echo "smoke rc=$? $(tail -1 gpurun_out/v8/smoke.log)"
-C=$(ls streams/c5_1080p_s*.ivf)
-for mode in new ref; do
-  if [ $mode = ref ]; then export VP8B200_TOKENS=ref; else unset VP8B200_TOKENS; fi
-  VP8B200_SYNC=block hostdec/_build/b200bench --threads 64 --streams 64 --repeat 4 $C > gpurun_out/v8/e2e_block_$mode.json
-  VP8B200_NO_DEVICE=1 hostdec/_build/b200bench --threads 64 --streams 64 --repeat 4 $C > gpurun_out/v8/parse_only_$mode.json
-done
-unset VP8B200_TOKENS
-VP8B200_SYNC=block hostdec/_build/b200bench --threads 32 --streams 64 --repeat 4 $C > gpurun_out/v8/e2e_block_new_t32.json
-VP8B200_SYNC=block hostdec/_build/b200bench --threads 128 --streams 128 --repeat 3 $C > gpurun_out/v8/e2e_block_new_s128.json
-python bench.py --impl reference > gpurun_out/v8/bench_ref.json 2> gpurun_out/v8/bench_ref.err
-python bench.py > gpurun_out/v8/bench.json 2> gpurun_out/v8/bench.err
-B="python bench.py --steps 4 --warmup 2 --skip-e2e --skip-verify --no-cpu-baseline --groups 1"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/v8/r01_launches_v8.csv $B > gpurun_out/v8/ncu1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_loopfilter -s 3 -c 1 -f -o gpurun_out/v8/r01_lf_v8 $B > gpurun_out/v8/ncu2.log 2>&1
-for f in gpurun_out/v8/*.json; do echo "== $f"; cat $f; echo; done
-python tools/config_table.py --out gpurun_out/v8/r01_configs.json > gpurun_out/v8/cfg.log 2>&1; tail -6 gpurun_out/v8/cfg.log | cut -c1-400
+# round-end measurement set (run under gpurun): GPU tests, smoke, both bench arms, ncu full captures of
+# the three big kernels and the launch list of a bench run.  Evidence is copied to profiles/ by hand.
+O=gpurun_out/final; mkdir -p $O
+timeout 1500 python -m pytest tests -m gpu -x -q --timeout 300 > $O/tests_gpu.log 2>&1; echo "gpu tests rc=$? $(tail -1 $O/tests_gpu.log)"
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$? $(tail -1 $O/smoke.log)"
+timeout 900 python bench.py > $O/bench_default.json 2> $O/bench_default.err; echo "bench default rc=$?"; tail -c 1500 $O/bench_default.json
+timeout 900 python bench.py --impl reference > $O/bench_reference.json 2> $O/bench_reference.err; echo "bench reference rc=$?"; tail -c 600 $O/bench_reference.json
+B2="python bench.py --steps 4 --warmup 2 --skip-e2e --skip-verify --no-cpu-baseline --no-extra --groups 1"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_inter16 -s 2 -c 1 -f -o $O/r02_inter $B2 > $O/ncu_inter.log 2>&1; echo "ncu inter rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_loopfilter -s 3 -c 1 -f -o $O/r02_lf $B2 > $O/ncu_lf.log 2>&1; echo "ncu lf rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_intra -s 0 -c 4 -f -o $O/r02_intra python bench.py --steps 2 --warmup 0 --skip-e2e --skip-verify --no-cpu-baseline --no-extra --groups 1 --stagger 0 > $O/ncu_intra.log 2>&1; echo "ncu intra rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02_launches.csv python bench.py --steps 6 --warmup 3 --skip-e2e --skip-verify --no-cpu-baseline --no-extra > $O/launch.log 2>&1; echo "ncu launches rc=$?"
