@@ -396,7 +396,9 @@ def run_b200(args):
 def run_e2e(args, clips, mine, local_rank, dist, dev, shard, S):
     # two worker threads per host core, each advancing its streams round-robin and collecting a
     # frame only after it has parsed its other streams (measured best on 16 cores: profiles/r02_summary.md)
-    threads = args.e2e_threads or min(S, 2 * (os.cpu_count() or 1))
+    # ... of the cores this rank can count on: the ranks of one node share them
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    threads = args.e2e_threads or min(S, max(2, 2 * (os.cpu_count() or 1) // world))
     repeat = max(1, args.e2e_repeat)
     env = dict(os.environ, VP8B200_DEVICE=str(local_rank), VP8B200_SYNC="block")
     cmd = [os.path.join(HOSTDEC, "b200bench"), "--threads", str(threads), "--streams", str(S),
