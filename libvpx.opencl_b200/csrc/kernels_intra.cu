@@ -361,23 +361,20 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
             }
         }
         __syncwarp();
-        /* ---- DC value (reconintra.c:167-195, :434-462) when this phase's mode is DC_PRED:
-         * lanes 0-15 sum luma, 16-23 U, 24-31 V ---- */
+        /* ---- DC value (reconintra.c:167-195, :434-462) when this phase's mode is DC_PRED ---- */
         int dc = 128;
         if ((phase == 0 ? (!bpred && mb.y_mode == VP8B200_DC_PRED) : mb.uv_mode == VP8B200_DC_PRED) && (up || left)) {
+            /* ONE warp reduction: the luma sum of lanes 0-15 (phase 0), or the U sum of lanes
+             * 16-23 in the low half and the V sum of lanes 24-31 in the high half (phase 1) */
             const uint8_t *T = lane < 16 ? YT : (lane < 24 ? UT : VT);
             const int ts = lane < 16 ? YS : CS, i = lane < 16 ? lane : (lane & 7);
-            int sum = (up ? T[-ts + i] : 0) + (left ? T[i * ts - 1] : 0);
-            /* segmented sums: 16 lanes, 8 lanes, 8 lanes */
-            sum += __shfl_xor_sync(FULL_MASK, sum, 1);
-            sum += __shfl_xor_sync(FULL_MASK, sum, 2);
-            sum += __shfl_xor_sync(FULL_MASK, sum, 4);
-            if (lane < 16) sum += __shfl_xor_sync(0xffffu, sum, 8);
-            const int shift = (lane < 16 ? 3 : 2) + (up ? 1 : 0) + (left ? 1 : 0);
-            dc = (sum + (1 << (shift - 1))) >> shift;
-            /* the V sum sits in lanes 24-31, the V blocks are predicted by lanes 20-23 */
-            const int dc_v = __shfl_sync(FULL_MASK, dc, 24);
-            if (lane >= 20) dc = dc_v;
+            const unsigned mine_sum = (unsigned)((up ? T[-ts + i] : 0) + (left ? T[i * ts - 1] : 0));
+            const bool in_phase = (lane < 16) == (phase == 0);
+            const unsigned sums = __reduce_add_sync(FULL_MASK, in_phase ? mine_sum << (lane >= 24 ? 16 : 0) : 0u);
+            const int shift = (phase == 0 ? 3 : 2) + (up ? 1 : 0) + (left ? 1 : 0);
+            /* luma blocks are predicted by lanes 0-15, U by 16-19, V by 20-23 */
+            const unsigned sum = (phase == 1 && lane >= 20) ? sums >> 16 : sums & 0xffffu;
+            dc = (int)(sum + (1u << (shift - 1))) >> shift;
         }
         if (phase == 0) {
             if (!bpred) {
@@ -387,8 +384,7 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
                     unsigned px[4];
                     block_mode(mb.y_mode, YT, YS, bx, by, dc, px);
                     if (has_res) add_parked(px);
-                    store4x4(dy + by * g.y_stride + bx, g.y_stride, px);
-                    store4x4(YT + by * YS + bx, YS, px);              /* for the export below */
+                    store4x4(YT + by * YS + bx, YS, px);              /* for the export below; the frame gets it after the hand-off */
                 }
             } else {
                 /* Per step one shared-memory load per lane - lane p of a block fetches element p
@@ -436,8 +432,7 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
             unsigned px[4];
             block_mode(mb.uv_mode, lane < 20 ? UT : VT, CS, bx, by, dc, px);
             if (has_res) add_parked(px);
-            store4x4((lane < 20 ? du : dv) + by * g.uv_stride + bx, g.uv_stride, px);
-            store4x4((lane < 20 ? UT : VT) + by * CS + bx, CS, px);   /* for the export below */
+            store4x4((lane < 20 ? UT : VT) + by * CS + bx, CS, px);   /* for the export below; the frame gets it after the hand-off */
         }
         /* ---- export this plane's bottom row + right column for the neighbours still to come ---- */
         __syncwarp();
@@ -456,10 +451,15 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
             unsigned long long *p = job.intra_msg + (size_t)mbi * 16 + lane;
             asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
         }
-        /* the finished B_PRED 16x16 goes out row by row, after the hand-off */
-        if (phase == 0 && bpred && lane < 16) {
+        /* the finished plane goes out to the frame row by row, AFTER the hand-off: the export
+         * must not queue behind these stores */
+        if (phase == 0 && lane < 16) {
             const unsigned *r = reinterpret_cast<const unsigned *>(YT + lane * YS);
             *reinterpret_cast<uint4 *>(dy + lane * g.y_stride) = make_uint4(r[0], r[1], r[2], r[3]);
+        }
+        if (phase == 1 && lane >= 16) {
+            const unsigned *r = reinterpret_cast<const unsigned *>((lane < 24 ? UT : VT) + (lane & 7) * CS);
+            *reinterpret_cast<uint2 *>((lane < 24 ? du : dv) + (lane & 7) * g.uv_stride) = make_uint2(r[0], r[1]);
         }
     }
 }

@@ -19,7 +19,7 @@ sys.path.insert(0, os.path.join(ROOT, "libvpx.opencl_b200")); sys.path.insert(0,
 import bench
 from vp8b200 import abi, recfile
 
-CONFIGS = [("c1_cif", os.path.join(ROOT, "tests", "golden", "cif_p0.ivf"), 64),
+CONFIGS = [("c1_cif", os.path.join(ROOT, "tests", "golden", "c1_cif.ivf"), 64),
            ("c2_720p", os.path.join(bench.STREAMS, "c2_720p.ivf"), 64),
            ("c3_1080p_p3", os.path.join(bench.STREAMS, "c3_1080p_p3.ivf"), 64),
            ("c3b_1080p_p1", os.path.join(bench.STREAMS, "c3b_1080p_p1.ivf"), 64),
