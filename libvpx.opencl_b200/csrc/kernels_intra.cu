@@ -202,20 +202,30 @@ k_intra(const FrameJob *__restrict__ jobs, const int n_jobs, const Geo g, const 
     bool has_res = false;
     if (lane < 24) has_res = block_residual(job, mb, lane, !bpred, res);
     if (lane < 24) {                                     /* parked in shared memory until the block is predicted */
+        /* clamp(pixel + r, 0, 255) == clamp(pixel + clamp(r, -255, 255), 0, 255) for a pixel in
+         * 0..255: clamping here, off the chain, lets the add after the wait be a packed 16x2 one */
+#pragma unroll
+        for (int i = 0; i < 16; i++) res[i] = max(min(res[i], 255), -255);
         uint4 *o = reinterpret_cast<uint4 *>(s_res[warp][lane]);
         o[0] = make_uint4((res[0] & 0xffff) | (res[1] << 16), (res[2] & 0xffff) | (res[3] << 16),
                           (res[4] & 0xffff) | (res[5] << 16), (res[6] & 0xffff) | (res[7] << 16));
         o[1] = make_uint4((res[8] & 0xffff) | (res[9] << 16), (res[10] & 0xffff) | (res[11] << 16),
                           (res[12] & 0xffff) | (res[13] << 16), (res[14] & 0xffff) | (res[15] << 16));
     }
+    /* four rows of four pixels + the parked residual, two pixels per instruction: expand two
+     * bytes to 16x2 (PRMT), add (VIADD.16x2), clamp to 0..255 (VIMNMX.S16x2), pack (PRMT) */
     auto add_parked = [&](unsigned (&px)[4]) {
-        int cr[16];
         const uint4 *q = reinterpret_cast<const uint4 *>(s_res[warp][lane]);
         const uint4 q0 = q[0], q1 = q[1];
         const unsigned qw[8] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w };
 #pragma unroll
-        for (int i = 0; i < 8; i++) { cr[2 * i] = (short)(qw[i] & 0xffff); cr[2 * i + 1] = (int)qw[i] >> 16; }
-        add_res(px, cr);
+        for (int r = 0; r < 4; r++) {
+            unsigned lo = __vadd2(__byte_perm(px[r], 0, 0x4140), qw[2 * r]);
+            unsigned hi = __vadd2(__byte_perm(px[r], 0, 0x4342), qw[2 * r + 1]);
+            lo = __vmins2(__vmaxs2(lo, 0u), 0x00ff00ffu);
+            hi = __vmins2(__vmaxs2(hi, 0u), 0x00ff00ffu);
+            px[r] = __byte_perm(lo, hi, 0x6420);
+        }
     };
     if (bpred && lane < 16) s_modes[warp][lane] = reinterpret_cast<const uint8_t *>(job.aux + mb.u.aux)[lane];
     const int pix = lane & 15, pr = pix >> 2, pc = pix & 3, which = lane >> 4;
