@@ -42,7 +42,7 @@
 #endif
 static_assert(1 + (LF_ROWS_PER_CTA - 1) * LF_RING <= 16, "one named barrier per (row pair, ring slot)");
 #ifndef LF_PF
-#define LF_PF 8                   /* cp.async prefetch distance in macroblocks (power of two, >= 2; 2: 1.1 ms, 4: 0.61, 8: 0.50, 16: 0.50 per 64x1080p) */
+#define LF_PF 16                  /* cp.async prefetch distance in macroblocks (power of two, >= 2; per 64x1080p launch: 2: 1.1 ms, 4: 0.77, 8: 0.49, 16: 0.465; 32 would cost a resident CTA) */
 #endif
 
 __device__ __forceinline__ int sc(int v) { return max(min(v, 127), -128); }
